@@ -1,0 +1,190 @@
+"""CPU-only tests that pin the oracle (oracle/oracle.c) before anything trusts it.
+
+Digest half: pinned by NIST FIPS 180-4 known answers and by hashlib (OpenSSL).
+Boundary half: PARITY UNPINNED against the Go module (absent, see oracle.c header);
+pinned here only by (i) two independent restatements agreeing (rolling C vs
+closed-form C vs vectorised numpy), (ii) split-invariance of the streaming scan(),
+(iii) the min/max invariants, (iv) committed golden vectors made by the oracle
+itself (tests/golden/make_golden.py) that freeze today's behaviour.
+"""
+import hashlib
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import pyref
+
+GOLDEN = Path(__file__).parent / "golden"
+
+
+def rnd(n, seed):
+    return np.random.default_rng(seed).integers(0, 256, size=n, dtype=np.uint8)
+
+
+NIST = [
+    (b"", "e3b0c44298fc1c149afbf4c8996fb92427ae41e4649b934ca495991b7852b855"),
+    (b"abc", "ba7816bf8f01cfea414140de5dae2223b00361a396177a9cb410ff61f20015ad"),
+    (b"abcdbcdecdefdefgefghfghighijhijkijkljklmklmnlmnomnopnopq",
+     "248d6a61d20638b8e5c026930c3e6039a33ce45964ff2167f6ecedd419db06c1"),
+    (b"a" * 1_000_000, "cdc76e5c9914fb9281a1c7e284d73e67f1809a48a497200e046d39ccc7112cd0"),
+]
+
+
+@pytest.mark.parametrize("portable", [False, True])
+def test_sha256_nist_vectors(portable):
+    oracle.force_portable_sha(portable)
+    try:
+        for msg, hexd in NIST:
+            assert oracle.sha256(np.frombuffer(msg, dtype=np.uint8)).hex() == hexd
+    finally:
+        oracle.force_portable_sha(False)
+
+
+@pytest.mark.parametrize("portable", [False, True])
+def test_sha256_vs_hashlib_all_small_lengths(portable):
+    oracle.force_portable_sha(portable)
+    try:
+        data = rnd(4096, 1)
+        for n in list(range(0, 260)) + [511, 512, 513, 4095, 4096]:
+            assert oracle.sha256(data[:n]) == hashlib.sha256(data[:n].tobytes()).digest(), n
+    finally:
+        oracle.force_portable_sha(False)
+
+
+def test_config_semantics():
+    cfg = oracle.config(4 << 20)
+    assert (cfg.avg, cfg.min, cfg.max) == (4 << 20, 1 << 20, 16 << 20)
+    assert cfg.mask == 0x7FFFFF and cfg.break_min == 0x7FFFFD and cfg.window == 64
+    for bad in (0, 3000, 255, 128, (1 << 30)):
+        with pytest.raises(ValueError):
+            oracle.config(bad)
+
+
+def test_default_table_fingerprint():
+    t = oracle.default_table()
+    assert t.shape == (256,) and t[0] == 0x458BE752 and len(set(t.tolist())) == 256
+    # fingerprint a maintainer can diff against the Go module's table (little-endian u32s)
+    fp = hashlib.sha256(t.astype("<u4").tobytes()).hexdigest()
+    assert fp == json.loads((GOLDEN / "table_fingerprint.json").read_text())["sha256_le_u32"]
+
+
+def test_rolling_equals_closed_form_window():
+    table = oracle.default_table()
+    data = rnd(5000, 2)
+    hs = pyref.window_hashes(table, data)
+    for i in (63, 64, 100, 1000, 4999):
+        assert oracle.window_hash(table, data[i - 63: i + 1]) == int(hs[i])
+
+
+@pytest.mark.parametrize("avg", [256, 1024, 4096])
+@pytest.mark.parametrize("seed", [3, 4])
+def test_three_restatements_agree(avg, seed):
+    table = oracle.default_table()
+    cfg = oracle.config(avg)
+    data = rnd(300_000 if avg <= 1024 else 1_000_000, seed)
+    a = oracle.chunk_ends(cfg, data).tolist()
+    b = oracle.chunk_ends_closed_form(cfg, data).tolist()
+    c = pyref.chunk_ends(table, data, avg)
+    assert a == b == c
+    assert a[-1] == len(data)
+
+
+def test_split_invariance_of_streaming_scan():
+    cfg = oracle.config(1024)
+    data = rnd(200_000, 5)
+    ref = oracle.chunk_ends(cfg, data).tolist()
+    for feed in (1, 7, 63, 64, 65, 1000, 4096, 99_999):
+        assert oracle.chunk_ends(cfg, data, feed=feed).tolist() == ref, feed
+
+
+def test_min_max_invariants_and_forced_cuts():
+    cfg = oracle.config(256)
+    # constant data: H == 0 for a full window, never passes the test -> every cut is forced at max
+    data = np.zeros(10_000, dtype=np.uint8)
+    ends = oracle.chunk_ends(cfg, data).tolist()
+    assert ends == list(range(1024, 10_000, 1024)) + [10_000]
+    data = rnd(500_000, 6)
+    ends = np.array([0] + oracle.chunk_ends(cfg, data).tolist())
+    lens = np.diff(ends)
+    assert (lens[:-1] >= cfg.min).all() and (lens <= cfg.max).all() and lens[-1] >= 1
+
+
+def test_edge_lengths():
+    cfg = oracle.config(256)
+    assert oracle.chunk_ends(cfg, np.zeros(0, np.uint8)).tolist() == []
+    for n in (1, 63, 64, 65, 255, 256, 257, 1023, 1024, 1025):
+        d = rnd(n, n)
+        e = oracle.chunk_ends(cfg, d).tolist()
+        assert e[-1] == n and e == pyref.chunk_ends(oracle.default_table(), d, 256)
+
+
+def test_custom_table_is_honoured():
+    t = np.random.default_rng(9).integers(0, 2**32, size=256, dtype=np.uint32)
+    cfg = oracle.config(512, t)
+    d = rnd(100_000, 10)
+    assert oracle.chunk_ends(cfg, d).tolist() == pyref.chunk_ends(t, d, 512)
+    assert oracle.chunk_ends(cfg, d).tolist() != oracle.chunk_ends(oracle.config(512), d).tolist()
+
+
+def test_chunk_digest_records():
+    cfg = oracle.config(1024)
+    d = rnd(150_000, 11)
+    rec = oracle.chunk_digest(cfg, d, stream=7)
+    ends = oracle.chunk_ends(cfg, d).tolist()
+    assert rec["end_off"].tolist() == ends and (rec["stream"] == 7).all()
+    assert [bytes(x) for x in rec["digest"]] == pyref.chunk_digests(d, ends)
+    many = oracle.chunk_digest_streams(cfg, [d, d[:5000], d[:0], d[100:]], threads=3)
+    assert many["stream"].tolist().count(0) == len(ends) and 2 not in many["stream"].tolist()
+    assert (many[many["stream"] == 0]["digest"] == rec["digest"]).all()
+
+
+def test_digest_set_semantics():
+    s = oracle.DigestSet(4)
+    d = np.random.default_rng(12).integers(0, 256, size=(1000, 32), dtype=np.uint8)
+    d[500:600] = d[0:100]                                   # in-batch duplicates
+    hit = s.probe(d, insert=True)
+    assert hit[:500].sum() == 0 and hit[500:600].all() and hit[600:].sum() == 0 and len(s) == 900
+    assert s.probe(d, insert=False).all()
+    assert not s.probe(np.zeros((1, 32), np.uint8), insert=False)[0]
+
+
+def test_corpus_generator_properties():
+    c = oracle.corpus(seed=2, file_len=1 << 16, block_len=1 << 12, run_blocks=2, dup_permille=300)
+    f0 = oracle.corpus_file(c, 0)
+    assert (oracle.corpus_file(c, 0, 1000, 5000) == f0[1000:6000]).all()      # random access == sequential
+    assert not (f0 == oracle.corpus_file(c, 1)).all()
+    files = oracle.corpus_files(c, 0, 40, threads=4)
+    assert (files[0] == f0).all()
+    blocks = np.concatenate(files).reshape(-1, 1 << 12)
+    uniq = len({b.tobytes() for b in blocks})
+    frac_dup = 1 - uniq / len(blocks)
+    assert 0.15 < frac_dup < 0.45                                             # ~30 % duplicate blocks
+    # incompressible-looking: byte histogram roughly flat
+    hist = np.bincount(f0, minlength=256)
+    assert hist.min() > 150 and hist.max() < 370
+    e1 = oracle.corpus(seed=2, file_len=1 << 16, block_len=1 << 12, run_blocks=2, dup_permille=300, edit_mode=1)
+    g0 = oracle.corpus_file(e1, 0)
+    assert 0.005 < (g0 != f0).mean() < 0.015                                  # ~1 % of bytes edited
+    e2 = oracle.corpus(seed=2, file_len=1 << 20, block_len=1 << 12, run_blocks=2, edit_mode=2)
+    base = oracle.corpus(seed=2, file_len=1 << 20, block_len=1 << 12, run_blocks=2)
+    diff = np.nonzero(oracle.corpus_file(e2, 3) != oracle.corpus_file(base, 3))[0]
+    assert 0 < len(diff) <= 12 and len(set((diff // (1 << 12)).tolist())) == len(diff)   # one byte per edited block
+
+
+def test_golden_vectors():
+    """Golden JSONL in the format SURVEY.md 8c defines; produced by the restated oracle
+    (tests/golden/make_golden.py), so it freezes behaviour -- it does not pin parity with Go."""
+    lines = (GOLDEN / "chunks_oracle.jsonl").read_text().splitlines()
+    assert len(lines) >= 6
+    for ln in lines:
+        g = json.loads(ln)
+        assert g["oracle"] == "restatement"
+        c = oracle.corpus(seed=g["seed"], file_len=g["len"], block_len=g["block_len"])
+        data = oracle.corpus_file(c, g["file_id"])
+        rec = oracle.chunk_digest(oracle.config(g["avg"]), data)
+        assert rec["end_off"].tolist() == g["cuts"]
+        assert [bytes(x).hex() for x in rec["digest"]] == g["digests"]
+        assert hashlib.sha256(data.tobytes()).hexdigest() == g["data_sha256"]
