@@ -1,0 +1,188 @@
+/*
+ * pbsgpu.h -- C ABI of libpbsgpu.so, the B200-native chunk + digest + probe engine.
+ *
+ * This is the drop-in boundary for the ONE hot path of pbs-plus that this repo
+ * accelerates: content-defined chunking (buzhash), per-chunk
+ * SHA-256 and the known-digest probe.  The reference (pbs-plus @ 26d6969) is pure
+ * Go with CGO disabled and has NO existing FFI for this path; the arithmetic sits
+ * behind Go call sites into github.com/pbs-plus/pxar v0.19.2 (reference go.mod:28).
+ * Every entry point below names the reference interface it replaces
+ * (paths relative to the reference tree).  The cgo binding a maintainer would add
+ * is in go/gpuchunk/ and INTEGRATION.md.
+ *
+ * Conventions: plain C, plain pointers and sizes, no C++/torch types.  Every
+ * function returns 0 on success or a negative PBSGPU_E* code; pbsgpu_strerror(ctx)
+ * returns the message of the last failure on that context.  No thread-local state:
+ * a ctx may be used from any OS thread (goroutines migrate), one call at a time per
+ * ctx; different ctxs are independent.  There is NO CPU fallback: if no CUDA device
+ * is usable pbsgpu_open fails.
+ */
+#ifndef PBSGPU_H
+#define PBSGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PBSGPU_VERSION 100 /* 0.1.0 */
+
+/* error codes (negative errno values) */
+#define PBSGPU_OK 0
+#define PBSGPU_EINVAL (-22)  /* bad argument (avg not a power of two, NULL, ...)      */
+#define PBSGPU_ENOMEM (-12)  /* host or device allocation failed                      */
+#define PBSGPU_ERANGE (-34)  /* caller's output array too small; *n_out = needed      */
+#define PBSGPU_ECUDA (-5)    /* CUDA runtime/driver error, see pbsgpu_strerror        */
+#define PBSGPU_ENODEV (-19)  /* no usable CUDA device                                 */
+#define PBSGPU_ESTATE (-77)  /* call not valid in this state (stream finished, ...)   */
+
+typedef struct pbsgpu_ctx pbsgpu_ctx;
+typedef struct pbsgpu_set pbsgpu_set;
+typedef struct pbsgpu_job pbsgpu_job;
+typedef struct pbsgpu_stream pbsgpu_stream;
+
+/* Chunker parameters.  Replaces buzhash.Config as built by buzhash.NewConfig(4096)
+ * at internal/pxarmount/commit.go:302-305 and handed to backupproxy.NewPBSStore at
+ * commit.go:296-305.  Derivation = upstream PBS ChunkerImpl::new. */
+typedef struct pbsgpu_cfg {
+    uint32_t avg;       /* average chunk size, BYTES, power of two, 256 .. 2^29 */
+    uint32_t min;       /* avg >> 2                                            */
+    uint32_t max;       /* avg << 2                                            */
+    uint32_t mask;      /* 2*avg - 1                                           */
+    uint32_t break_min; /* mask - 2 : cut iff (h & mask) >= break_min           */
+    uint32_t window;    /* 64                                                  */
+    uint32_t table[256];
+} pbsgpu_cfg;
+
+/* One finished chunk.  Replaces the (end offset, digest) pair the reference's
+ * dedup writer appends to the dynamic index for every chunk produced inside
+ * transfer.ArchiveWriter.WriteEntryReader (commit.go:720, :858). */
+typedef struct pbsgpu_chunk {
+    uint32_t stream;    /* index of the input stream in this call                */
+    uint32_t flags;     /* PBSGPU_CHUNK_KNOWN: digest already in the set (skip upload) */
+    uint64_t end_off;   /* exclusive end offset of the chunk within its stream   */
+    uint8_t digest[32]; /* SHA-256 of the raw chunk bytes (CryptModeNone, commit.go:314) */
+} pbsgpu_chunk;
+#define PBSGPU_CHUNK_KNOWN 1u
+
+typedef struct pbsgpu_devinfo {
+    int32_t device;
+    int32_t sm_count;
+    int32_t cc_major, cc_minor;
+    uint64_t total_mem, free_mem;
+    char name[64];
+} pbsgpu_devinfo;
+
+/* Device-time breakdown of the last finished batch/job, CUDA events on the
+ * launching stream (only filled when profiling is on). */
+typedef struct pbsgpu_timing {
+    float scan_ms, sort_ms, resolve_ms, sha_ms, set_ms, total_ms;
+    /* kernel intervals in ms since the context was opened (same CUDA clock for all jobs of
+     * a ctx): lets a caller merge overlapping jobs into "time a kernel class was active" */
+    float scan_t0, scan_t1, sha_t0, sha_t1;
+    uint64_t bytes, chunks, candidates;
+    uint32_t scan_launches, sha_launches, other_launches, reruns;
+} pbsgpu_timing;
+
+/* ---- lifecycle -------------------------------------------------------------- */
+int pbsgpu_version(void);
+int pbsgpu_open(int device, pbsgpu_ctx **out);
+void pbsgpu_close(pbsgpu_ctx *ctx);
+const char *pbsgpu_strerror(const pbsgpu_ctx *ctx);
+int pbsgpu_device_info(pbsgpu_ctx *ctx, pbsgpu_devinfo *out);
+int pbsgpu_set_profiling(pbsgpu_ctx *ctx, int on);
+/* 0 = tuned kernels (default), 1 = simple cross-check kernels (same results) */
+int pbsgpu_set_kernel_variant(pbsgpu_ctx *ctx, int variant);
+
+/* ---- a1: configuration (replaces buzhash.NewConfig, commit.go:302-305) ------- */
+/* avg in BYTES; table NULL = built-in default table. */
+int pbsgpu_config(uint32_t avg_bytes, const uint32_t *table /*[256] or NULL*/, pbsgpu_cfg *out);
+/* The reference passes 4096 = KiB in the upstream client's convention (4 MiB). */
+int pbsgpu_config_kib(uint32_t avg_kib, const uint32_t *table, pbsgpu_cfg *out);
+const uint32_t *pbsgpu_default_table(void);
+
+/* ---- a2+a3(+a4): batch of independent streams ---------------------------------
+ * Replaces, for n files at once, the per-file loop
+ *     writer.WriteEntryReader(entry, reader, size)       (commit.go:720, :858)
+ * i.e. [pull bytes -> buzhash scan -> cut -> SHA-256(chunk) -> known?].
+ * Stream i is bytes [base+off[i], base+off[i]+len[i]).  `base` may be a DEVICE
+ * pointer (data already resident in HBM) or a HOST pointer (pageable or pinned;
+ * the library stages it through pinned buffers and overlaps H2D with compute).
+ * Chunks are returned ordered by (stream, end_off).  If `set` is non-NULL every
+ * chunk digest is probed against it in that order (a digest also counts as known
+ * if an earlier chunk of the same call had it) and then inserted.
+ * Returns PBSGPU_ERANGE with *n_out = required count if cap is too small. */
+int pbsgpu_chunk_digest_batch(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg, const void *base, const uint64_t *off,
+                              const uint64_t *len, uint32_t n, pbsgpu_set *set, pbsgpu_chunk *out, uint64_t cap,
+                              uint64_t *n_out);
+
+/* Asynchronous form for DEVICE-resident input: submit returns as soon as the
+ * kernels are enqueued; several jobs may be in flight (they overlap on the GPU,
+ * which hides the sequential tail of the longest chunk's SHA-256).  wait blocks,
+ * copies the chunks out and frees the job.  `set` must be NULL here (probe order
+ * across overlapping jobs would be undefined); probe after wait. */
+int pbsgpu_batch_submit(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg, const void *base_dev, const uint64_t *off,
+                        const uint64_t *len, uint32_t n, pbsgpu_job **job);
+int pbsgpu_batch_wait(pbsgpu_job *job, pbsgpu_chunk *out, uint64_t cap, uint64_t *n_out, pbsgpu_timing *timing);
+
+/* Boundary scan only (a2): chunk END offsets per stream, no digests.
+ * ends: caller array of cap u64; stream_first[i]..stream_first[i+1] index it
+ * (stream_first has n+1 entries). */
+int pbsgpu_scan_batch(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg, const void *base, const uint64_t *off,
+                      const uint64_t *len, uint32_t n, uint64_t *ends, uint64_t cap, uint64_t *stream_first,
+                      uint64_t *n_out);
+
+/* Digest only (a3): SHA-256 of n arbitrary byte ranges; digests = n*32 bytes (host). */
+int pbsgpu_sha256_batch(pbsgpu_ctx *ctx, const void *base, const uint64_t *off, const uint64_t *len, uint32_t n,
+                        uint8_t *digests);
+
+/* ---- streaming form -----------------------------------------------------------
+ * Mirrors how the reference feeds ONE io.Reader of known size through the chunker
+ * (scan() state carried across reads; commit.go:718-720).  Bytes are buffered on
+ * the device; finished chunks become available from poll(); finish() emits the
+ * final short chunk.  Results are identical to the batch call on the whole stream
+ * no matter how the bytes are split across writes. */
+int pbsgpu_stream_open(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg, pbsgpu_set *set, pbsgpu_stream **out);
+int pbsgpu_stream_write(pbsgpu_stream *s, const void *host_data, uint64_t len);
+int pbsgpu_stream_poll(pbsgpu_stream *s, pbsgpu_chunk *out, uint64_t cap, uint64_t *n_out);
+int pbsgpu_stream_finish(pbsgpu_stream *s);
+void pbsgpu_stream_close(pbsgpu_stream *s);
+
+/* ---- a4: known-digest set -------------------------------------------------------
+ * Replaces the known-chunk bookkeeping of the reference's dedup session:
+ * seeded from the previous snapshot (backupproxy.PreviousBackupRef commit.go:286-294,
+ * origPayloadIdx commit.go:324-329), "Only new chunks are uploaded"
+ * (docs/pxar-mount.md:105).  Exact 32-byte comparison, device-resident table. */
+int pbsgpu_set_create(pbsgpu_ctx *ctx, uint64_t capacity_hint, pbsgpu_set **out);
+void pbsgpu_set_destroy(pbsgpu_set *set);
+/* d32: n*32 bytes, HOST or DEVICE pointer.  hit (HOST, n bytes, may be NULL):
+ * 1 = already present before this call or earlier within it. */
+int pbsgpu_set_insert(pbsgpu_set *set, const uint8_t *d32, uint64_t n, uint8_t *hit);
+int pbsgpu_set_probe(pbsgpu_set *set, const uint8_t *d32, uint64_t n, uint8_t *hit);
+int pbsgpu_set_count(pbsgpu_set *set, uint64_t *count);
+/* Seed from a PBS dynamic index (.didx) image: 4096-byte header + 40-byte
+ * {u64 end_le, digest[32]} entries (what origPayloadIdx holds, commit.go:324-329). */
+int pbsgpu_set_seed_didx(pbsgpu_set *set, const uint8_t *didx, uint64_t size, uint64_t *n_entries);
+
+/* ---- pinned staging owned by C, filled by the Go side ----------------------------- */
+void *pbsgpu_host_alloc(pbsgpu_ctx *ctx, uint64_t bytes);
+void pbsgpu_host_free(pbsgpu_ctx *ctx, void *p);
+
+/* ---- measurement aid: synthetic corpus generated on the device ------------------
+ * Same integer recipe as oracle/oracle.c:orc_corpus_fill.
+ * Writes files [first_file, first_file+n_files), each file_len bytes, at
+ * dst_dev + i*stride. */
+typedef struct pbsgpu_corpus {
+    uint64_t seed, file_len, block_len;
+    uint32_t run_blocks, dup_permille, edit_mode, edit_thresh16;
+    uint64_t edit_seed;
+} pbsgpu_corpus;
+int pbsgpu_corpus_fill(pbsgpu_ctx *ctx, const pbsgpu_corpus *c, uint64_t first_file, uint32_t n_files,
+                       void *dst_dev, uint64_t stride);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PBSGPU_H */

@@ -1,0 +1,960 @@
+// pbs_plus_b200/csrc/capi.cu -- C ABI (include/pbsgpu.h) and host orchestration.
+//
+// Host side of the drop-in boundary: what a Go caller reaches through cgo in place of
+// buzhash.NewConfig / backupproxy.NewPBSStore / transfer...WriteEntryReader of the
+// reference (internal/pxarmount/commit.go:296-329, :720).  Pure C++ over the CUDA
+// runtime; no torch types.  There is no CPU fallback anywhere in this file: every data
+// path launches the kernels in scan.cu / resolve.cu / sha256.cu / digestset.cu.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cub/device/device_radix_sort.cuh>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "internal.cuh"
+
+using namespace pbsgpu;
+
+static const uint32_t DEFAULT_TABLE[256] = {
+#include "default_table.inc"
+};
+
+// ---------------------------------------------------------------------------
+// small caching allocators (device + pinned host): steady-state batches do not
+// hit cudaMalloc / cudaHostAlloc.
+// ---------------------------------------------------------------------------
+struct Block { void *p; size_t size; bool used; };
+struct Pool {
+    std::vector<Block> blocks;
+    bool pinned = false;
+    void *get(size_t need) {
+        need = (need + 255) & ~(size_t)255;
+        if (need == 0) need = 256;
+        int best = -1;
+        for (size_t i = 0; i < blocks.size(); i++)
+            if (!blocks[i].used && blocks[i].size >= need && blocks[i].size <= need * 2 + 4096 &&
+                (best < 0 || blocks[i].size < blocks[best].size)) best = (int)i;
+        if (best >= 0) { blocks[best].used = true; return blocks[best].p; }
+        void *p = nullptr;
+        cudaError_t e = pinned ? cudaHostAlloc(&p, need, cudaHostAllocDefault) : cudaMalloc(&p, need);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            trim();   // drop cached free blocks and retry once
+            e = pinned ? cudaHostAlloc(&p, need, cudaHostAllocDefault) : cudaMalloc(&p, need);
+            if (e != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+        }
+        blocks.push_back({p, need, true});
+        return p;
+    }
+    void put(void *p) {
+        if (!p) return;
+        for (auto &b : blocks) if (b.p == p) { b.used = false; return; }
+    }
+    void trim() {
+        std::vector<Block> keep;
+        for (auto &b : blocks) {
+            if (b.used) keep.push_back(b);
+            else if (pinned) cudaFreeHost(b.p); else cudaFree(b.p);
+        }
+        blocks.swap(keep);
+    }
+    void destroy() {
+        for (auto &b : blocks) { if (pinned) cudaFreeHost(b.p); else cudaFree(b.p); }
+        blocks.clear();
+    }
+};
+
+constexpr int N_STREAMS = 4;
+
+struct pbsgpu_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaDeviceProp prop;
+    std::string err;
+    std::recursive_mutex mu;
+    cudaStream_t streams[N_STREAMS];
+    cudaStream_t copy_stream;
+    int next_stream = 0;
+    Pool dev, pin;
+    bool profiling = false;
+    int variant = 0;
+    // device copies of the chunker table (re-uploaded when the cfg table changes)
+    uint32_t *d_table = nullptr, *d_rot = nullptr;
+    uint32_t table_cache[256];
+    bool table_valid = false;
+    pbsgpu_timing last_timing;
+    cudaEvent_t epoch = nullptr;   // recorded at open; kernel intervals are reported relative to it
+    uint64_t stage_bytes = 0;   // host-input staging size (0 = auto)
+};
+
+static int fail(pbsgpu_ctx *c, int code, const char *fmt, ...) {
+    if (c) {
+        char buf[512];
+        va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+        c->err = buf;
+    }
+    return code;
+}
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e__ = (call);                                                                      \
+        if (e__ != cudaSuccess) {                                                                      \
+            (void)cudaGetLastError();                                                                  \
+            return fail(ctx, PBSGPU_ECUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+        }                                                                                              \
+    } while (0)
+#define CKDEV(ctx) CK(cudaSetDevice((ctx)->device))
+
+struct Guard {   // one call at a time per ctx + device binding for this OS thread (goroutines migrate)
+    std::lock_guard<std::recursive_mutex> lk;
+    explicit Guard(pbsgpu_ctx *c) : lk(c->mu) { cudaSetDevice(c->device); }
+};
+
+// ---------------------------------------------------------------------------
+extern "C" int pbsgpu_version(void) { return PBSGPU_VERSION; }
+extern "C" const uint32_t *pbsgpu_default_table(void) { return DEFAULT_TABLE; }
+
+extern "C" int pbsgpu_config(uint32_t avg, const uint32_t *table, pbsgpu_cfg *out) {
+    if (!out || avg < 256u || avg > (1u << 29) || (avg & (avg - 1))) return PBSGPU_EINVAL;
+    out->avg = avg; out->min = avg >> 2; out->max = avg << 2;
+    out->mask = avg * 2u - 1u; out->break_min = out->mask - 2u; out->window = 64;
+    memcpy(out->table, table ? table : DEFAULT_TABLE, sizeof out->table);
+    return PBSGPU_OK;
+}
+extern "C" int pbsgpu_config_kib(uint32_t avg_kib, const uint32_t *table, pbsgpu_cfg *out) {
+    if (avg_kib == 0 || avg_kib > (1u << 19)) return PBSGPU_EINVAL;
+    return pbsgpu_config(avg_kib << 10, table, out);
+}
+static bool cfg_ok(const pbsgpu_cfg *c) {
+    return c && c->avg >= 256u && c->avg <= (1u << 29) && !(c->avg & (c->avg - 1)) && c->min == c->avg >> 2 &&
+           c->max == c->avg << 2 && c->mask == c->avg * 2u - 1u && c->break_min == c->mask - 2u && c->window == 64;
+}
+
+extern "C" int pbsgpu_open(int device, pbsgpu_ctx **out) {
+    if (!out) return PBSGPU_EINVAL;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { (void)cudaGetLastError(); return PBSGPU_ENODEV; }
+    if (device < 0 || device >= n) return PBSGPU_ENODEV;
+    pbsgpu_ctx *ctx = new pbsgpu_ctx();
+    ctx->device = device;
+    ctx->dev.pinned = false; ctx->pin.pinned = true;
+    memset(&ctx->last_timing, 0, sizeof ctx->last_timing);
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&ctx->prop, device) != cudaSuccess) {
+        (void)cudaGetLastError(); delete ctx; return PBSGPU_ENODEV;
+    }
+    ctx->sm_count = ctx->prop.multiProcessorCount;
+    for (int i = 0; i < N_STREAMS; i++)
+        if (cudaStreamCreateWithFlags(&ctx->streams[i], cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PBSGPU_ECUDA; }
+    if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PBSGPU_ECUDA; }
+    if (cudaMalloc(&ctx->d_table, 1024) != cudaSuccess || cudaMalloc(&ctx->d_rot, 65536) != cudaSuccess) {
+        delete ctx; return PBSGPU_ENOMEM;
+    }
+    if (cudaEventCreate(&ctx->epoch) != cudaSuccess || cudaEventRecord(ctx->epoch, ctx->streams[0]) != cudaSuccess ||
+        cudaEventSynchronize(ctx->epoch) != cudaSuccess) { delete ctx; return PBSGPU_ECUDA; }
+    const char *sb = getenv("PBSGPU_STAGE_BYTES");
+    if (sb) ctx->stage_bytes = strtoull(sb, nullptr, 0);
+    const char *v = getenv("PBSGPU_VARIANT");
+    if (v) ctx->variant = atoi(v);
+    *out = ctx;
+    return PBSGPU_OK;
+}
+
+extern "C" void pbsgpu_close(pbsgpu_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < N_STREAMS; i++) cudaStreamDestroy(ctx->streams[i]);
+    cudaStreamDestroy(ctx->copy_stream);
+    cudaFree(ctx->d_table); cudaFree(ctx->d_rot);
+    if (ctx->epoch) cudaEventDestroy(ctx->epoch);
+    ctx->dev.destroy(); ctx->pin.destroy();
+    delete ctx;
+}
+
+extern "C" const char *pbsgpu_strerror(const pbsgpu_ctx *ctx) {
+    if (!ctx) return "pbsgpu: no context (pbsgpu_open failed: no usable CUDA device?)";
+    return ctx->err.c_str();
+}
+
+extern "C" int pbsgpu_device_info(pbsgpu_ctx *ctx, pbsgpu_devinfo *out) {
+    if (!ctx || !out) return PBSGPU_EINVAL;
+    Guard g(ctx);
+    memset(out, 0, sizeof *out);
+    out->device = ctx->device; out->sm_count = ctx->sm_count;
+    out->cc_major = ctx->prop.major; out->cc_minor = ctx->prop.minor;
+    size_t fr = 0, tot = 0;
+    CK(cudaMemGetInfo(&fr, &tot));
+    out->free_mem = fr; out->total_mem = tot;
+    strncpy(out->name, ctx->prop.name, sizeof out->name - 1);
+    return PBSGPU_OK;
+}
+extern "C" int pbsgpu_set_profiling(pbsgpu_ctx *ctx, int on) { if (!ctx) return PBSGPU_EINVAL; ctx->profiling = on != 0; return 0; }
+extern "C" int pbsgpu_set_kernel_variant(pbsgpu_ctx *ctx, int v) { if (!ctx || v < 0 || v > 1) return PBSGPU_EINVAL; ctx->variant = v; return 0; }
+
+extern "C" void *pbsgpu_host_alloc(pbsgpu_ctx *ctx, uint64_t bytes) {
+    if (!ctx) return nullptr;
+    Guard g(ctx);
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+    return p;
+}
+extern "C" void pbsgpu_host_free(pbsgpu_ctx *ctx, void *p) { if (ctx && p) { Guard g(ctx); cudaFreeHost(p); } }
+
+static int upload_table(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg, cudaStream_t st) {
+    if (ctx->table_valid && memcmp(ctx->table_cache, cfg->table, 1024) == 0) return PBSGPU_OK;
+    // all streams must be done with the old table before it is replaced
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpyAsync(ctx->d_table, cfg->table, 1024, cudaMemcpyHostToDevice, st));
+    CK(launch_build_rot_table(ctx->d_table, ctx->d_rot, st));
+    CK(cudaStreamSynchronize(st));
+    memcpy(ctx->table_cache, cfg->table, 1024);
+    ctx->table_valid = true;
+    return PBSGPU_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Job: one batch of device-resident streams through K1..K3 on one CUDA stream.
+// ---------------------------------------------------------------------------
+enum { EV_START, EV_SCAN, EV_SORT, EV_RESOLVE, EV_SHA, EV_END, EV_COUNT };
+
+struct pbsgpu_job {
+    pbsgpu_ctx *ctx = nullptr;
+    cudaStream_t st = nullptr;
+    pbsgpu_cfg cfg;
+    const uint8_t *base = nullptr;
+    std::vector<uint64_t> off, len, tile_first;
+    uint32_t n = 0;
+    uint64_t total_bytes = 0, total_tiles = 0, chunk_cap = 0, cand_cap = 0;
+    int eof = 1, want_digests = 1, variant = 0;
+    // device
+    uint64_t *d_off = nullptr, *d_len = nullptr, *d_tile_first = nullptr, *d_cand = nullptr, *d_cand_sorted = nullptr;
+    unsigned long long *d_counters = nullptr;   // [0] cand_count [1] n_chunks
+    uint32_t *d_counts = nullptr;
+    uint64_t *d_chunk_first = nullptr, *d_consumed = nullptr;
+    ChunkRef *d_chunks = nullptr;
+    uint32_t *d_keys = nullptr, *d_keys2 = nullptr, *d_vals = nullptr, *d_vals2 = nullptr;
+    uint8_t *d_digests = nullptr;
+    pbsgpu_chunk *d_out = nullptr;
+    void *d_temp = nullptr; size_t temp_bytes = 0;
+    // pinned host
+    unsigned long long *h_counters = nullptr;
+    pbsgpu_chunk *h_out = nullptr;
+    uint64_t *h_consumed = nullptr;
+    cudaEvent_t ev[EV_COUNT];
+    bool have_events = false, profiling = false, enqueued = false;
+    uint32_t reruns = 0;
+};
+
+static void job_release(pbsgpu_job *j) {
+    if (!j) return;
+    pbsgpu_ctx *c = j->ctx;
+    void *devp[] = {j->d_off, j->d_len, j->d_tile_first, j->d_cand, j->d_cand_sorted, j->d_counters, j->d_counts,
+                    j->d_chunk_first, j->d_consumed, j->d_chunks, j->d_keys, j->d_keys2, j->d_vals, j->d_vals2,
+                    j->d_digests, j->d_out, j->d_temp};
+    for (void *p : devp) c->dev.put(p);
+    c->pin.put(j->h_counters); c->pin.put(j->h_out); c->pin.put(j->h_consumed);
+    if (j->have_events) for (int i = 0; i < EV_COUNT; i++) cudaEventDestroy(j->ev[i]);
+    delete j;
+}
+
+static uint64_t expected_cand_cap(const pbsgpu_cfg &cfg, uint64_t total) {
+    // candidates occur with probability 3/(mask+1) per byte on random data
+    long double e = (long double)total * 3.0L / ((long double)cfg.mask + 1.0L);
+    uint64_t cap = (uint64_t)(e * 4.0L) + 4096;
+    return cap;
+}
+
+static int job_alloc(pbsgpu_job *j) {
+    pbsgpu_ctx *ctx = j->ctx;
+    Pool &d = ctx->dev;
+    const uint32_t n = j->n;
+#define DALLOC(ptr, type, count)                                                           \
+    do {                                                                                   \
+        ptr = (type *)d.get(sizeof(type) * (size_t)(count));                               \
+        if (!ptr) return fail(ctx, PBSGPU_ENOMEM, "device allocation of %zu bytes failed", \
+                              sizeof(type) * (size_t)(count));                             \
+    } while (0)
+    DALLOC(j->d_off, uint64_t, n + 1);
+    DALLOC(j->d_len, uint64_t, n + 1);
+    DALLOC(j->d_tile_first, uint64_t, n + 2);
+    DALLOC(j->d_cand, uint64_t, j->cand_cap);
+    DALLOC(j->d_cand_sorted, uint64_t, j->cand_cap);
+    DALLOC(j->d_counters, unsigned long long, 4);
+    DALLOC(j->d_counts, uint32_t, n + 1);
+    DALLOC(j->d_chunk_first, uint64_t, n + 2);
+    DALLOC(j->d_consumed, uint64_t, n + 1);
+    DALLOC(j->d_chunks, ChunkRef, j->chunk_cap + 1);
+    DALLOC(j->d_out, pbsgpu_chunk, j->chunk_cap + 1);
+    if (j->want_digests) {
+        DALLOC(j->d_keys, uint32_t, j->chunk_cap + 1);
+        DALLOC(j->d_keys2, uint32_t, j->chunk_cap + 1);
+        DALLOC(j->d_vals, uint32_t, j->chunk_cap + 1);
+        DALLOC(j->d_vals2, uint32_t, j->chunk_cap + 1);
+        DALLOC(j->d_digests, uint8_t, (j->chunk_cap + 1) * 32);
+    }
+    size_t t1 = 0, t2 = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, t1, (uint64_t *)nullptr, (uint64_t *)nullptr, (int)j->cand_cap);
+    if (j->want_digests)
+        cub::DeviceRadixSort::SortPairsDescending(nullptr, t2, (uint32_t *)nullptr, (uint32_t *)nullptr,
+                                                  (uint32_t *)nullptr, (uint32_t *)nullptr, (int)j->chunk_cap);
+    j->temp_bytes = std::max(t1, t2) + 256;
+    DALLOC(j->d_temp, uint8_t, j->temp_bytes);
+#undef DALLOC
+    j->h_counters = (unsigned long long *)ctx->pin.get(4 * sizeof(unsigned long long));
+    j->h_out = (pbsgpu_chunk *)ctx->pin.get(sizeof(pbsgpu_chunk) * (j->chunk_cap + 1));
+    j->h_consumed = (uint64_t *)ctx->pin.get(sizeof(uint64_t) * (n + 1));
+    if (!j->h_counters || !j->h_out || !j->h_consumed) return fail(ctx, PBSGPU_ENOMEM, "pinned host allocation failed");
+    return PBSGPU_OK;
+}
+
+static int job_create(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg, const void *base_dev, const uint64_t *off,
+                      const uint64_t *len, uint32_t n, int eof, int want_digests, pbsgpu_job **out) {
+    if (!cfg_ok(cfg)) return fail(ctx, PBSGPU_EINVAL, "invalid pbsgpu_cfg (use pbsgpu_config)");
+    if (n >= (1u << 24)) return fail(ctx, PBSGPU_EINVAL, "too many streams in one batch (%u >= 2^24)", n);
+    pbsgpu_job *j = new pbsgpu_job();
+    j->ctx = ctx; j->cfg = *cfg; j->base = (const uint8_t *)base_dev; j->n = n; j->eof = eof;
+    j->want_digests = want_digests; j->variant = ctx->variant; j->profiling = ctx->profiling;
+    j->off.assign(off, off + n); j->len.assign(len, len + n);
+    const uint64_t tile = j->variant == 1 ? (uint64_t)SIMPLE_SPAN : (uint64_t)WARP_TILE;
+    j->tile_first.resize(n + 1);
+    uint64_t tiles = 0, total = 0, chunks = 0;
+    const uint64_t min_eff = min_effective(cfg->min);
+    for (uint32_t i = 0; i < n; i++) {
+        if (len[i] >= (1ull << KEY_POS_BITS)) { delete j; return fail(ctx, PBSGPU_EINVAL, "stream %u longer than 2^40 bytes", i); }
+        j->tile_first[i] = tiles;
+        tiles += (len[i] + tile - 1) / tile;
+        total += len[i];
+        chunks += len[i] / min_eff + 1;
+    }
+    j->tile_first[n] = tiles;
+    j->total_tiles = tiles; j->total_bytes = total; j->chunk_cap = chunks;
+    if (chunks >= (1ull << 31)) { delete j; return fail(ctx, PBSGPU_EINVAL, "batch too large (%llu chunk slots)", (unsigned long long)chunks); }
+    j->cand_cap = expected_cand_cap(*cfg, total);
+    if (j->cand_cap >= (1ull << 31)) { delete j; return fail(ctx, PBSGPU_EINVAL, "batch too large (candidate buffer)"); }
+    j->st = ctx->streams[ctx->next_stream];
+    ctx->next_stream = (ctx->next_stream + 1) % N_STREAMS;
+    int rc = job_alloc(j);
+    if (rc) { job_release(j); return rc; }
+    for (int i = 0; i < EV_COUNT; i++)
+        if (cudaEventCreateWithFlags(&j->ev[i], j->profiling ? cudaEventDefault : cudaEventDisableTiming) != cudaSuccess) {
+            for (int k = 0; k < i; k++) cudaEventDestroy(j->ev[k]);
+            job_release(j);
+            return fail(ctx, PBSGPU_ECUDA, "cudaEventCreate failed");
+        }
+    j->have_events = true;
+    *out = j;
+    return PBSGPU_OK;
+}
+
+static int job_enqueue(pbsgpu_job *j) {
+    pbsgpu_ctx *ctx = j->ctx;
+    cudaStream_t st = j->st;
+    const uint32_t n = j->n;
+    int rc = upload_table(ctx, &j->cfg, st);
+    if (rc) return rc;
+    if (n) {
+        CK(cudaMemcpyAsync(j->d_off, j->off.data(), n * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(j->d_len, j->len.data(), n * 8, cudaMemcpyHostToDevice, st));
+    }
+    CK(cudaMemcpyAsync(j->d_tile_first, j->tile_first.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(j->d_counters, 0, 4 * sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(j->d_cand, 0xFF, j->cand_cap * 8, st));   // KEY_SENTINEL padding for the sort
+    if (j->profiling) CK(cudaEventRecord(j->ev[EV_START], st));
+    // K1
+    ScanArgs sa;
+    sa.base = j->base; sa.off = j->d_off; sa.len = j->d_len; sa.tile_first = j->d_tile_first; sa.n_streams = n;
+    sa.total_tiles = j->total_tiles; sa.mask = j->cfg.mask; sa.break_min = j->cfg.break_min; sa.table = ctx->d_table;
+    sa.cand = j->d_cand; sa.cand_cap = j->cand_cap; sa.cand_count = &j->d_counters[0];
+    if (j->variant == 1) CK(launch_scan_simple(sa, st));
+    else CK(launch_scan_tuned(sa, ctx->d_rot, ctx->sm_count, st));
+    if (j->profiling) CK(cudaEventRecord(j->ev[EV_SCAN], st));
+    // candidates -> sorted by (stream, position)
+    size_t tb = j->temp_bytes;
+    CK(cub::DeviceRadixSort::SortKeys(j->d_temp, tb, j->d_cand, j->d_cand_sorted, (int)j->cand_cap, 0, 64, st));
+    if (j->profiling) CK(cudaEventRecord(j->ev[EV_SORT], st));
+    // K2
+    ResolveArgs ra;
+    ra.keys_sorted = j->d_cand_sorted; ra.cand_count = &j->d_counters[0]; ra.cand_cap = j->cand_cap; ra.len = j->d_len;
+    ra.n_streams = n; ra.cmin = j->cfg.min; ra.cmax = j->cfg.max; ra.eof = j->eof; ra.counts = j->d_counts;
+    ra.chunk_first = j->d_chunk_first; ra.chunks = j->d_chunks; ra.chunk_cap = j->chunk_cap; ra.consumed = j->d_consumed;
+    ra.n_chunks = &j->d_counters[1];
+    CK(launch_resolve(ra, st));
+    if (j->profiling) CK(cudaEventRecord(j->ev[EV_RESOLVE], st));
+    // K3
+    if (j->want_digests && j->chunk_cap) {
+        CK(launch_len_keys(j->d_chunks, &j->d_counters[1], j->chunk_cap, j->d_keys, j->d_vals, st));
+        tb = j->temp_bytes;
+        CK(cub::DeviceRadixSort::SortPairsDescending(j->d_temp, tb, j->d_keys, j->d_keys2, j->d_vals, j->d_vals2,
+                                                     (int)j->chunk_cap, 0, 32, st));
+        ShaArgs ha;
+        ha.base = j->base; ha.off = j->d_off; ha.chunks = j->d_chunks; ha.order = j->d_vals2;
+        ha.n_chunks = &j->d_counters[1]; ha.chunk_cap = j->chunk_cap; ha.digests = j->d_digests;
+        if (j->variant == 1) CK(launch_sha_simple(ha, st));
+        else CK(launch_sha_tuned(ha, ctx->sm_count, st));
+    }
+    if (j->profiling) CK(cudaEventRecord(j->ev[EV_SHA], st));
+    if (j->want_digests)
+        CK(launch_pack_chunks(j->d_chunks, j->d_digests, nullptr, &j->d_counters[1], j->chunk_cap, j->d_out, st));
+    CK(cudaMemcpyAsync(j->h_counters, j->d_counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    if (j->want_digests)
+        CK(cudaMemcpyAsync(j->h_out, j->d_out, sizeof(pbsgpu_chunk) * j->chunk_cap, cudaMemcpyDeviceToHost, st));
+    if (!j->eof && n) CK(cudaMemcpyAsync(j->h_consumed, j->d_consumed, n * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(j->ev[EV_END], st));
+    j->enqueued = true;
+    return PBSGPU_OK;
+}
+
+// Blocks until the job is done; reruns it with a larger candidate buffer if the
+// (statistically sized) one overflowed -- results are exact either way.
+static int job_finish(pbsgpu_job *j) {
+    pbsgpu_ctx *ctx = j->ctx;
+    for (;;) {
+        CK(cudaEventSynchronize(j->ev[EV_END]));
+        unsigned long long nc = j->h_counters[0];
+        if (nc <= j->cand_cap) break;
+        // dense candidates (adversarial / highly structured data): grow and redo
+        ctx->dev.put(j->d_cand); ctx->dev.put(j->d_cand_sorted); ctx->dev.put(j->d_temp);
+        j->d_cand = j->d_cand_sorted = nullptr; j->d_temp = nullptr;
+        j->cand_cap = nc + nc / 8 + 4096;
+        if (j->cand_cap >= (1ull << 31)) return fail(ctx, PBSGPU_ENOMEM, "candidate density too high (%llu candidates)", nc);
+        j->d_cand = (uint64_t *)ctx->dev.get(j->cand_cap * 8);
+        j->d_cand_sorted = (uint64_t *)ctx->dev.get(j->cand_cap * 8);
+        size_t t1 = 0, t2 = 0;
+        cub::DeviceRadixSort::SortKeys(nullptr, t1, (uint64_t *)nullptr, (uint64_t *)nullptr, (int)j->cand_cap);
+        if (j->want_digests)
+            cub::DeviceRadixSort::SortPairsDescending(nullptr, t2, (uint32_t *)nullptr, (uint32_t *)nullptr,
+                                                      (uint32_t *)nullptr, (uint32_t *)nullptr, (int)j->chunk_cap);
+        j->temp_bytes = std::max(t1, t2) + 256;
+        j->d_temp = ctx->dev.get(j->temp_bytes);
+        if (!j->d_cand || !j->d_cand_sorted || !j->d_temp) return fail(ctx, PBSGPU_ENOMEM, "device allocation failed (rerun)");
+        j->reruns++;
+        int rc = job_enqueue(j);
+        if (rc) return rc;
+    }
+    pbsgpu_timing &t = ctx->last_timing;
+    memset(&t, 0, sizeof t);
+    t.bytes = j->total_bytes; t.chunks = j->h_counters[1]; t.candidates = j->h_counters[0]; t.reruns = j->reruns;
+    t.scan_launches = 1; t.sha_launches = j->want_digests ? 1 : 0; t.other_launches = 3 + (j->want_digests ? 2 : 0);
+    if (j->profiling) {
+        cudaEventElapsedTime(&t.scan_ms, j->ev[EV_START], j->ev[EV_SCAN]);
+        cudaEventElapsedTime(&t.sort_ms, j->ev[EV_SCAN], j->ev[EV_SORT]);
+        cudaEventElapsedTime(&t.resolve_ms, j->ev[EV_SORT], j->ev[EV_RESOLVE]);
+        cudaEventElapsedTime(&t.sha_ms, j->ev[EV_RESOLVE], j->ev[EV_SHA]);
+        cudaEventElapsedTime(&t.total_ms, j->ev[EV_START], j->ev[EV_END]);
+        cudaEventElapsedTime(&t.scan_t0, ctx->epoch, j->ev[EV_START]);
+        cudaEventElapsedTime(&t.scan_t1, ctx->epoch, j->ev[EV_SCAN]);
+        cudaEventElapsedTime(&t.sha_t0, ctx->epoch, j->ev[EV_RESOLVE]);
+        cudaEventElapsedTime(&t.sha_t1, ctx->epoch, j->ev[EV_SHA]);
+    }
+    return PBSGPU_OK;
+}
+
+static bool is_device_ptr(const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+extern "C" int pbsgpu_batch_submit(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg, const void *base_dev, const uint64_t *off,
+                                   const uint64_t *len, uint32_t n, pbsgpu_job **job) {
+    if (!ctx || !job || (n && (!off || !len))) return PBSGPU_EINVAL;
+    Guard g(ctx);
+    *job = nullptr;
+    if (n && !is_device_ptr(base_dev)) return fail(ctx, PBSGPU_EINVAL, "pbsgpu_batch_submit needs a device pointer");
+    pbsgpu_job *j = nullptr;
+    int rc = job_create(ctx, cfg, base_dev, off, len, n, 1, 1, &j);
+    if (rc) return rc;
+    rc = job_enqueue(j);
+    if (rc) { cudaStreamSynchronize(j->st); job_release(j); return rc; }
+    *job = j;
+    return PBSGPU_OK;
+}
+
+extern "C" int pbsgpu_batch_wait(pbsgpu_job *j, pbsgpu_chunk *out, uint64_t cap, uint64_t *n_out, pbsgpu_timing *timing) {
+    if (!j) return PBSGPU_EINVAL;
+    pbsgpu_ctx *ctx = j->ctx;
+    Guard g(ctx);
+    int rc = job_finish(j);
+    if (rc == PBSGPU_OK) {
+        uint64_t nch = j->h_counters[1];
+        if (n_out) *n_out = nch;
+        if (timing) *timing = ctx->last_timing;
+        if (nch > cap) rc = fail(ctx, PBSGPU_ERANGE, "output capacity %llu < %llu chunks", (unsigned long long)cap, (unsigned long long)nch);
+        else if (nch) memcpy(out, j->h_out, nch * sizeof(pbsgpu_chunk));
+    } else {
+        cudaStreamSynchronize(j->st);
+    }
+    job_release(j);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------
+// digest set
+// ---------------------------------------------------------------------------
+struct pbsgpu_set {
+    pbsgpu_ctx *ctx;
+    SetTable t;
+    uint64_t count;
+};
+
+static int set_alloc_table(pbsgpu_ctx *ctx, uint64_t cap, SetTable *t) {
+    t->cap = cap;
+    t->tags = (uint64_t *)ctx->dev.get(cap * 8);
+    t->keys = (uint64_t *)ctx->dev.get(cap * 32);
+    if (!t->tags || !t->keys) return fail(ctx, PBSGPU_ENOMEM, "digest set allocation failed (%llu slots)", (unsigned long long)cap);
+    CK(cudaMemsetAsync(t->tags, 0, cap * 8, ctx->streams[0]));
+    return PBSGPU_OK;
+}
+
+extern "C" int pbsgpu_set_create(pbsgpu_ctx *ctx, uint64_t capacity_hint, pbsgpu_set **out) {
+    if (!ctx || !out) return PBSGPU_EINVAL;
+    Guard g(ctx);
+    uint64_t cap = 1024;
+    while (cap < capacity_hint * 2) cap <<= 1;
+    pbsgpu_set *s = new pbsgpu_set();
+    s->ctx = ctx; s->count = 0;
+    int rc = set_alloc_table(ctx, cap, &s->t);
+    if (rc) { delete s; return rc; }
+    CK(cudaStreamSynchronize(ctx->streams[0]));
+    *out = s;
+    return PBSGPU_OK;
+}
+extern "C" void pbsgpu_set_destroy(pbsgpu_set *s) {
+    if (!s) return;
+    Guard g(s->ctx);
+    cudaStreamSynchronize(s->ctx->streams[0]);
+    s->ctx->dev.put(s->t.tags); s->ctx->dev.put(s->t.keys);
+    delete s;
+}
+extern "C" int pbsgpu_set_count(pbsgpu_set *s, uint64_t *count) { if (!s || !count) return PBSGPU_EINVAL; *count = s->count; return 0; }
+
+// d_dig: device pointer to n*32 bytes.  d_hit: device n bytes or NULL.
+static int set_process_dev(pbsgpu_set *s, const uint8_t *d_dig, uint64_t n, int do_insert, uint8_t *d_hit) {
+    pbsgpu_ctx *ctx = s->ctx;
+    cudaStream_t st = ctx->streams[0];
+    if (n == 0) return PBSGPU_OK;
+    if (n >= (1ull << 31)) return fail(ctx, PBSGPU_EINVAL, "too many digests in one call");
+    if (do_insert && (s->count + n) * 2 > s->t.cap) {   // keep load <= 50 %
+        uint64_t cap = s->t.cap;
+        while ((s->count + n) * 2 > cap) cap <<= 1;
+        SetTable nt;
+        int rc = set_alloc_table(ctx, cap, &nt);
+        if (rc) return rc;
+        CK(launch_set_rehash(s->t, nt, st));
+        CK(cudaStreamSynchronize(st));
+        ctx->dev.put(s->t.tags); ctx->dev.put(s->t.keys);
+        s->t = nt;
+    }
+    uint64_t *tag = (uint64_t *)ctx->dev.get(n * 8), *tag2 = (uint64_t *)ctx->dev.get(n * 8);
+    uint32_t *idx = (uint32_t *)ctx->dev.get(n * 4), *idx2 = (uint32_t *)ctx->dev.get(n * 4);
+    uint8_t *miss = (uint8_t *)ctx->dev.get(n);
+    unsigned long long *d_new = (unsigned long long *)ctx->dev.get(8);
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, (uint64_t *)nullptr, (uint64_t *)nullptr, (uint32_t *)nullptr,
+                                    (uint32_t *)nullptr, (int)n);
+    void *temp = ctx->dev.get(tb + 256);
+    int rc = PBSGPU_OK;
+    unsigned long long h_new = 0;
+    auto cleanup = [&]() {
+        ctx->dev.put(tag); ctx->dev.put(tag2); ctx->dev.put(idx); ctx->dev.put(idx2); ctx->dev.put(miss);
+        ctx->dev.put(d_new); ctx->dev.put(temp);
+    };
+    if (!tag || !tag2 || !idx || !idx2 || !miss || !d_new || !temp) { cleanup(); return fail(ctx, PBSGPU_ENOMEM, "digest set scratch allocation failed"); }
+#define CKS(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { (void)cudaGetLastError(); cleanup(); \
+        return fail(ctx, PBSGPU_ECUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); } } while (0)
+    CKS(cudaMemsetAsync(d_new, 0, 8, st));
+    CKS(launch_set_make_keys(d_dig, n, tag, idx, st));
+    CKS(cub::DeviceRadixSort::SortPairs(temp, tb, tag, tag2, idx, idx2, (int)n, 0, 64, st));   // stable
+    CKS(launch_set_mark_probe_insert(s->t, d_dig, tag2, idx2, n, do_insert, d_hit, miss, d_new, st));
+    CKS(cudaMemcpyAsync(&h_new, d_new, 8, cudaMemcpyDeviceToHost, st));
+    CKS(cudaStreamSynchronize(st));
+#undef CKS
+    s->count += h_new;
+    cleanup();
+    return rc;
+}
+
+static int set_process(pbsgpu_set *s, const uint8_t *d32, uint64_t n, int do_insert, uint8_t *hit_host) {
+    if (!s || (n && !d32)) return PBSGPU_EINVAL;
+    pbsgpu_ctx *ctx = s->ctx;
+    Guard g(ctx);
+    if (n == 0) return PBSGPU_OK;
+    cudaStream_t st = ctx->streams[0];
+    const uint8_t *d_dig = d32;
+    uint8_t *staged = nullptr;
+    if (!is_device_ptr(d32)) {
+        staged = (uint8_t *)ctx->dev.get(n * 32);
+        if (!staged) return fail(ctx, PBSGPU_ENOMEM, "digest staging allocation failed");
+        CK(cudaMemcpyAsync(staged, d32, n * 32, cudaMemcpyHostToDevice, st));
+        d_dig = staged;
+    }
+    uint8_t *d_hit = hit_host ? (uint8_t *)ctx->dev.get(n) : nullptr;
+    int rc = set_process_dev(s, d_dig, n, do_insert, d_hit);
+    if (rc == PBSGPU_OK && hit_host) {
+        cudaError_t e = cudaMemcpy(hit_host, d_hit, n, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = fail(ctx, PBSGPU_ECUDA, "hit copy: %s", cudaGetErrorString(e));
+    }
+    ctx->dev.put(staged); ctx->dev.put(d_hit);
+    return rc;
+}
+extern "C" int pbsgpu_set_insert(pbsgpu_set *s, const uint8_t *d32, uint64_t n, uint8_t *hit) { return set_process(s, d32, n, 1, hit); }
+extern "C" int pbsgpu_set_probe(pbsgpu_set *s, const uint8_t *d32, uint64_t n, uint8_t *hit) { return set_process(s, d32, n, 0, hit); }
+
+extern "C" int pbsgpu_set_seed_didx(pbsgpu_set *s, const uint8_t *didx, uint64_t size, uint64_t *n_entries) {
+    if (!s || !didx) return PBSGPU_EINVAL;
+    pbsgpu_ctx *ctx = s->ctx;
+    if (size < 4096 || (size - 4096) % 40) return fail(ctx, PBSGPU_EINVAL, "not a dynamic index image (size %llu)", (unsigned long long)size);
+    uint64_t n = (size - 4096) / 40;
+    std::vector<uint8_t> dig(n * 32);
+    for (uint64_t i = 0; i < n; i++) memcpy(&dig[i * 32], didx + 4096 + i * 40 + 8, 32);
+    if (n_entries) *n_entries = n;
+    return set_process(s, dig.data(), n, 1, nullptr);
+}
+
+// flags for chunk records that are already on the host, in order
+static int apply_set(pbsgpu_set *set, pbsgpu_chunk *out, uint64_t n) {
+    if (!set || n == 0) return PBSGPU_OK;
+    std::vector<uint8_t> dig(n * 32), hit(n);
+    for (uint64_t i = 0; i < n; i++) memcpy(&dig[i * 32], out[i].digest, 32);
+    int rc = set_process(set, dig.data(), n, 1, hit.data());
+    if (rc) return rc;
+    for (uint64_t i = 0; i < n; i++) if (hit[i]) out[i].flags |= PBSGPU_CHUNK_KNOWN;
+    return PBSGPU_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Synchronous batch; host input is staged through device buffers, group by group,
+// H2D of group k+1 overlapping the kernels of group k.
+// ---------------------------------------------------------------------------
+struct Group { uint32_t first, count; uint64_t bytes; };
+
+static int batch_host(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg, const uint8_t *base, const uint64_t *off,
+                      const uint64_t *len, uint32_t n, pbsgpu_chunk *out, uint64_t cap, uint64_t *n_out) {
+    size_t fr = 0, tot = 0;
+    CK(cudaMemGetInfo(&fr, &tot));
+    uint64_t stage = ctx->stage_bytes ? ctx->stage_bytes : std::min<uint64_t>(4ull << 30, fr / 8);
+    auto al = [](uint64_t x) { return (x + 255) & ~255ull; };
+    std::vector<Group> groups;
+    {
+        Group g{0, 0, 0};
+        for (uint32_t i = 0; i < n; i++) {
+            uint64_t b = al(len[i]);
+            if (g.count && g.bytes + b > stage) { groups.push_back(g); g = Group{i, 0, 0}; }
+            g.count++; g.bytes += b;
+        }
+        if (g.count) groups.push_back(g);
+    }
+    constexpr int NBUF = 3;
+    uint64_t buf_bytes = 256;
+    for (auto &g : groups) buf_bytes = std::max(buf_bytes, g.bytes);
+    uint8_t *bufs[NBUF] = {nullptr, nullptr, nullptr};
+    int nbuf = (int)std::min<size_t>(NBUF, groups.size());
+    for (int b = 0; b < nbuf; b++) {
+        bufs[b] = (uint8_t *)ctx->dev.get(buf_bytes);
+        if (!bufs[b]) { for (int k = 0; k < b; k++) ctx->dev.put(bufs[k]); return fail(ctx, PBSGPU_ENOMEM, "staging buffer of %llu bytes failed", (unsigned long long)buf_bytes); }
+    }
+    std::vector<pbsgpu_job *> jobs(groups.size(), nullptr);
+    std::vector<cudaEvent_t> copied(groups.size());
+    for (auto &e : copied) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    int rc = PBSGPU_OK;
+    uint64_t produced = 0;
+    bool overflow = false;
+    auto collect = [&](size_t gi) -> int {
+        pbsgpu_job *j = jobs[gi];
+        int r = job_finish(j);
+        if (r == PBSGPU_OK) {
+            uint64_t nch = j->h_counters[1];
+            if (produced + nch > cap) overflow = true;
+            else {
+                for (uint64_t k = 0; k < nch; k++) {
+                    pbsgpu_chunk c = j->h_out[k];
+                    c.stream += groups[gi].first;
+                    out[produced + k] = c;
+                }
+            }
+            produced += nch;
+        } else cudaStreamSynchronize(j->st);
+        job_release(j);
+        jobs[gi] = nullptr;
+        return r;
+    };
+    for (size_t gi = 0; gi < groups.size() && rc == PBSGPU_OK; gi++) {
+        if (gi >= (size_t)nbuf) { rc = collect(gi - nbuf); if (rc) break; }   // frees the buffer we are about to reuse
+        const Group &g = groups[gi];
+        uint8_t *buf = bufs[gi % nbuf];
+        std::vector<uint64_t> goff(g.count), glen(g.count);
+        uint64_t pos = 0;
+        for (uint32_t k = 0; k < g.count; k++) {
+            uint32_t i = g.first + k;
+            goff[k] = pos; glen[k] = len[i];
+            if (len[i]) {
+                cudaError_t e = cudaMemcpyAsync(buf + pos, base + off[i], len[i], cudaMemcpyHostToDevice, ctx->copy_stream);
+                if (e != cudaSuccess) { rc = fail(ctx, PBSGPU_ECUDA, "H2D copy failed: %s", cudaGetErrorString(e)); break; }
+            }
+            pos += al(len[i]);
+        }
+        if (rc) break;
+        cudaEventRecord(copied[gi], ctx->copy_stream);
+        pbsgpu_job *j = nullptr;
+        rc = job_create(ctx, cfg, buf, goff.data(), glen.data(), g.count, 1, 1, &j);
+        if (rc) break;
+        cudaStreamWaitEvent(j->st, copied[gi], 0);
+        rc = job_enqueue(j);
+        if (rc) { cudaStreamSynchronize(j->st); job_release(j); break; }
+        jobs[gi] = j;
+    }
+    for (size_t gi = 0; gi < groups.size(); gi++)
+        if (jobs[gi]) { int r = collect(gi); if (rc == PBSGPU_OK) rc = r; }
+    cudaStreamSynchronize(ctx->copy_stream);
+    for (auto &e : copied) cudaEventDestroy(e);
+    for (int b = 0; b < nbuf; b++) ctx->dev.put(bufs[b]);
+    if (n_out) *n_out = produced;
+    if (rc == PBSGPU_OK && overflow)
+        rc = fail(ctx, PBSGPU_ERANGE, "output capacity %llu < %llu chunks", (unsigned long long)cap, (unsigned long long)produced);
+    return rc;
+}
+
+extern "C" int pbsgpu_chunk_digest_batch(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg, const void *base, const uint64_t *off,
+                                         const uint64_t *len, uint32_t n, pbsgpu_set *set, pbsgpu_chunk *out,
+                                         uint64_t cap, uint64_t *n_out) {
+    if (!ctx || (n && (!off || !len || !base)) || (cap && !out)) return PBSGPU_EINVAL;
+    if (set && set->ctx != ctx) return fail(ctx, PBSGPU_EINVAL, "set belongs to another context");
+    Guard g(ctx);
+    if (!cfg_ok(cfg)) return fail(ctx, PBSGPU_EINVAL, "invalid pbsgpu_cfg (use pbsgpu_config)");
+    uint64_t produced = 0;
+    int rc;
+    if (n == 0) { if (n_out) *n_out = 0; return PBSGPU_OK; }
+    if (is_device_ptr(base)) {
+        pbsgpu_job *j = nullptr;
+        rc = job_create(ctx, cfg, base, off, len, n, 1, 1, &j);
+        if (rc) return rc;
+        rc = job_enqueue(j);
+        if (rc == PBSGPU_OK) rc = job_finish(j);
+        if (rc == PBSGPU_OK) {
+            produced = j->h_counters[1];
+            if (produced > cap) rc = fail(ctx, PBSGPU_ERANGE, "output capacity %llu < %llu chunks", (unsigned long long)cap, (unsigned long long)produced);
+            else if (produced) memcpy(out, j->h_out, produced * sizeof(pbsgpu_chunk));
+        } else cudaStreamSynchronize(j->st);
+        job_release(j);
+    } else {
+        rc = batch_host(ctx, cfg, (const uint8_t *)base, off, len, n, out, cap, &produced);
+    }
+    if (n_out) *n_out = produced;
+    if (rc == PBSGPU_OK && set) rc = apply_set(set, out, produced);
+    return rc;
+}
+
+extern "C" int pbsgpu_scan_batch(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg, const void *base, const uint64_t *off,
+                                 const uint64_t *len, uint32_t n, uint64_t *ends, uint64_t cap, uint64_t *stream_first,
+                                 uint64_t *n_out) {
+    if (!ctx || (n && (!off || !len || !base)) || !stream_first) return PBSGPU_EINVAL;
+    Guard g(ctx);
+    if (!is_device_ptr(base) && n) return fail(ctx, PBSGPU_EINVAL, "pbsgpu_scan_batch needs a device pointer");
+    pbsgpu_job *j = nullptr;
+    int rc = job_create(ctx, cfg, base, off, len, n, 1, 0, &j);
+    if (rc) return rc;
+    rc = job_enqueue(j);
+    if (rc == PBSGPU_OK) rc = job_finish(j);
+    if (rc == PBSGPU_OK) {
+        uint64_t nch = j->h_counters[1];
+        if (n_out) *n_out = nch;
+        if (nch > cap) rc = fail(ctx, PBSGPU_ERANGE, "output capacity %llu < %llu chunks", (unsigned long long)cap, (unsigned long long)nch);
+        else {
+            std::vector<ChunkRef> refs(nch);
+            std::vector<uint64_t> first(n + 1);
+            cudaError_t e = cudaMemcpy(refs.data(), j->d_chunks, nch * sizeof(ChunkRef), cudaMemcpyDeviceToHost);
+            if (e == cudaSuccess) e = cudaMemcpy(first.data(), j->d_chunk_first, (n + 1) * 8, cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) rc = fail(ctx, PBSGPU_ECUDA, "D2H: %s", cudaGetErrorString(e));
+            else {
+                for (uint64_t k = 0; k < nch; k++) ends[k] = refs[k].start + refs[k].len;
+                memcpy(stream_first, first.data(), (n + 1) * 8);
+            }
+        }
+    } else cudaStreamSynchronize(j->st);
+    job_release(j);
+    return rc;
+}
+
+extern "C" int pbsgpu_sha256_batch(pbsgpu_ctx *ctx, const void *base, const uint64_t *off, const uint64_t *len,
+                                   uint32_t n, uint8_t *digests) {
+    if (!ctx || (n && (!off || !len || !digests))) return PBSGPU_EINVAL;
+    Guard g(ctx);
+    if (n == 0) return PBSGPU_OK;
+    cudaStream_t st = ctx->streams[0];
+    std::vector<ChunkRef> refs(n);
+    uint64_t hi = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        if (len[i] >= (1ull << 32)) return fail(ctx, PBSGPU_EINVAL, "range %u longer than 4 GiB", i);
+        refs[i].stream = i; refs[i].len = (uint32_t)len[i]; refs[i].start = off[i];
+        hi = std::max(hi, off[i] + len[i]);
+    }
+    const uint8_t *dbase = (const uint8_t *)base;
+    uint8_t *staged = nullptr;
+    if (!is_device_ptr(base)) {
+        staged = (uint8_t *)ctx->dev.get(hi + 16);
+        if (!staged) return fail(ctx, PBSGPU_ENOMEM, "staging of %llu bytes failed", (unsigned long long)hi);
+        CK(cudaMemcpyAsync(staged, base, hi, cudaMemcpyHostToDevice, st));
+        dbase = staged;
+    }
+    ChunkRef *d_refs = (ChunkRef *)ctx->dev.get(sizeof(ChunkRef) * n);
+    uint8_t *d_dig = (uint8_t *)ctx->dev.get((uint64_t)n * 32);
+    unsigned long long *d_n = (unsigned long long *)ctx->dev.get(8);
+    int rc = PBSGPU_OK;
+    if (!d_refs || !d_dig || !d_n) rc = fail(ctx, PBSGPU_ENOMEM, "device allocation failed");
+    else {
+        unsigned long long hn = n;
+        cudaError_t e = cudaMemcpyAsync(d_refs, refs.data(), sizeof(ChunkRef) * n, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_n, &hn, 8, cudaMemcpyHostToDevice, st);
+        ShaArgs ha;
+        ha.base = dbase; ha.off = nullptr; ha.chunks = d_refs; ha.order = nullptr; ha.n_chunks = d_n; ha.chunk_cap = n;
+        ha.digests = d_dig;
+        if (e == cudaSuccess) e = ctx->variant == 1 ? launch_sha_simple(ha, st) : launch_sha_tuned(ha, ctx->sm_count, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(digests, d_dig, (uint64_t)n * 32, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { (void)cudaGetLastError(); rc = fail(ctx, PBSGPU_ECUDA, "sha256 batch: %s", cudaGetErrorString(e)); }
+    }
+    ctx->dev.put(d_refs); ctx->dev.put(d_dig); ctx->dev.put(d_n); ctx->dev.put(staged);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------
+// streaming form
+// ---------------------------------------------------------------------------
+struct pbsgpu_stream {
+    pbsgpu_ctx *ctx;
+    pbsgpu_cfg cfg;
+    pbsgpu_set *set;
+    uint64_t window;        // process when this many bytes are buffered
+    uint64_t cap;           // device buffer capacity = window + max
+    uint8_t *buf[2];        // ping-pong (carry is copied to the other buffer)
+    int cur;
+    uint64_t fill;          // bytes buffered in buf[cur]
+    uint64_t base_off;      // stream offset of buf[cur][0]
+    bool finished, started;
+    std::vector<pbsgpu_chunk> ready;
+    size_t ready_pos;
+};
+
+extern "C" int pbsgpu_stream_open(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg, pbsgpu_set *set, pbsgpu_stream **out) {
+    if (!ctx || !out) return PBSGPU_EINVAL;
+    Guard g(ctx);
+    if (!cfg_ok(cfg)) return fail(ctx, PBSGPU_EINVAL, "invalid pbsgpu_cfg (use pbsgpu_config)");
+    pbsgpu_stream *s = new pbsgpu_stream();
+    s->ctx = ctx; s->cfg = *cfg; s->set = set;
+    uint64_t w = 256ull << 20;
+    const char *e = getenv("PBSGPU_STREAM_WINDOW");
+    if (e) w = strtoull(e, nullptr, 0);
+    s->window = std::max<uint64_t>(w, (uint64_t)cfg->max);
+    s->cap = 0; s->buf[0] = s->buf[1] = nullptr; s->cur = 0; s->fill = 0; s->base_off = 0;
+    s->finished = false; s->started = false; s->ready_pos = 0;
+    *out = s;
+    return PBSGPU_OK;
+}
+
+static int stream_process(pbsgpu_stream *s, int eof) {
+    pbsgpu_ctx *ctx = s->ctx;
+    if (s->fill == 0) return PBSGPU_OK;
+    uint64_t off0 = 0, len0 = s->fill;
+    pbsgpu_job *j = nullptr;
+    int rc = job_create(ctx, &s->cfg, s->buf[s->cur], &off0, &len0, 1, eof, 1, &j);
+    if (rc) return rc;
+    rc = job_enqueue(j);
+    if (rc == PBSGPU_OK) rc = job_finish(j);
+    if (rc != PBSGPU_OK) { cudaStreamSynchronize(j->st); job_release(j); return rc; }
+    uint64_t nch = j->h_counters[1];
+    uint64_t consumed = eof ? s->fill : j->h_consumed[0];
+    size_t before = s->ready.size();
+    for (uint64_t k = 0; k < nch; k++) {
+        pbsgpu_chunk c = j->h_out[k];
+        c.stream = 0; c.end_off += s->base_off;
+        s->ready.push_back(c);
+    }
+    job_release(j);
+    if (s->set && nch) { rc = apply_set(s->set, s->ready.data() + before, nch); if (rc) return rc; }
+    // carry the undecided tail to the other buffer
+    uint64_t rest = s->fill - consumed;
+    if (rest) {
+        CK(cudaMemcpyAsync(s->buf[s->cur ^ 1], s->buf[s->cur] + consumed, rest, cudaMemcpyDeviceToDevice, ctx->streams[0]));
+        CK(cudaStreamSynchronize(ctx->streams[0]));
+    }
+    s->cur ^= 1; s->fill = rest; s->base_off += consumed;
+    return PBSGPU_OK;
+}
+
+extern "C" int pbsgpu_stream_write(pbsgpu_stream *s, const void *data, uint64_t len) {
+    if (!s || (len && !data)) return PBSGPU_EINVAL;
+    pbsgpu_ctx *ctx = s->ctx;
+    Guard g(ctx);
+    if (s->finished) return fail(ctx, PBSGPU_ESTATE, "stream already finished");
+    if (!s->started) {
+        s->cap = s->window + s->cfg.max + 256;
+        s->buf[0] = (uint8_t *)ctx->dev.get(s->cap); s->buf[1] = (uint8_t *)ctx->dev.get(s->cap);
+        if (!s->buf[0] || !s->buf[1]) return fail(ctx, PBSGPU_ENOMEM, "stream buffers of %llu bytes failed", (unsigned long long)s->cap);
+        s->started = true;
+    }
+    const uint8_t *p = (const uint8_t *)data;
+    while (len) {
+        uint64_t room = s->cap - s->fill;
+        uint64_t take = std::min(len, std::min(room, s->window > s->fill ? s->window - s->fill : 0));
+        if (take == 0) {   // window full: process, keeping the undecided tail
+            int rc = stream_process(s, 0);
+            if (rc) return rc;
+            if (s->fill >= s->window) return fail(ctx, PBSGPU_ESTATE, "internal: stream window did not drain");
+            continue;
+        }
+        // ordered on one of our (non-blocking) streams and completed before any kernel may read it
+        CK(cudaMemcpyAsync(s->buf[s->cur] + s->fill, p, take, cudaMemcpyHostToDevice, ctx->streams[0]));
+        CK(cudaStreamSynchronize(ctx->streams[0]));
+        s->fill += take; p += take; len -= take;
+    }
+    if (s->fill >= s->window) return stream_process(s, 0);
+    return PBSGPU_OK;
+}
+
+extern "C" int pbsgpu_stream_finish(pbsgpu_stream *s) {
+    if (!s) return PBSGPU_EINVAL;
+    Guard g(s->ctx);
+    if (s->finished) return PBSGPU_OK;
+    int rc = stream_process(s, 1);
+    if (rc == PBSGPU_OK) s->finished = true;
+    return rc;
+}
+
+extern "C" int pbsgpu_stream_poll(pbsgpu_stream *s, pbsgpu_chunk *out, uint64_t cap, uint64_t *n_out) {
+    if (!s || !n_out || (cap && !out)) return PBSGPU_EINVAL;
+    Guard g(s->ctx);
+    uint64_t avail = s->ready.size() - s->ready_pos;
+    uint64_t k = std::min(avail, cap);
+    if (k) memcpy(out, s->ready.data() + s->ready_pos, k * sizeof(pbsgpu_chunk));
+    s->ready_pos += k;
+    if (s->ready_pos == s->ready.size()) { s->ready.clear(); s->ready_pos = 0; }
+    *n_out = k;
+    return PBSGPU_OK;
+}
+
+extern "C" void pbsgpu_stream_close(pbsgpu_stream *s) {
+    if (!s) return;
+    Guard g(s->ctx);
+    s->ctx->dev.put(s->buf[0]); s->ctx->dev.put(s->buf[1]);
+    delete s;
+}
+
+// ---------------------------------------------------------------------------
+extern "C" int pbsgpu_corpus_fill(pbsgpu_ctx *ctx, const pbsgpu_corpus *c, uint64_t first_file, uint32_t n_files,
+                                  void *dst_dev, uint64_t stride) {
+    if (!ctx || !c || !dst_dev) return PBSGPU_EINVAL;
+    Guard g(ctx);
+    if (c->block_len == 0 || c->block_len % 8 || c->run_blocks == 0 || ((uintptr_t)dst_dev & 7) || (stride & 7) ||
+        stride < c->file_len)
+        return fail(ctx, PBSGPU_EINVAL, "corpus: block_len %% 8, run_blocks >= 1, 8-byte aligned dst/stride >= file_len required");
+    CK(launch_corpus_fill(*c, first_file, n_files, (uint8_t *)dst_dev, stride, ctx->streams[0]));
+    CK(cudaStreamSynchronize(ctx->streams[0]));
+    return PBSGPU_OK;
+}

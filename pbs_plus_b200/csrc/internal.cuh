@@ -1,0 +1,101 @@
+// pbs_plus_b200/csrc/internal.cuh -- declarations shared by the kernels and the C ABI.
+// Product code: never includes anything under oracle/.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pbsgpu.h"
+
+namespace pbsgpu {
+
+// Candidate keys: (stream << 40) | position.  Limits: position < 2^40 (1 TiB per
+// stream), stream index < 2^24.
+constexpr int KEY_POS_BITS = 40;
+constexpr uint64_t KEY_POS_MASK = (1ull << KEY_POS_BITS) - 1;
+constexpr uint64_t KEY_SENTINEL = ~0ull;
+
+// upstream scan() tests only after the 64-byte window is full AND has rolled once
+__host__ __device__ inline uint32_t min_effective(uint32_t cmin) { return cmin > 64u ? cmin : 65u; }
+
+struct ChunkRef {      // device-side chunk descriptor produced by resolve
+    uint32_t stream;
+    uint32_t len;      // <= max chunk size <= 2^31
+    uint64_t start;    // offset within stream
+};
+
+// ---- scan (K1) ---------------------------------------------------------------
+// Tuned kernel geometry: one warp owns a tile of 32 lanes x LANE_SPAN bytes.
+constexpr int LANE_SPAN = 272;               // 17 x 16 B: conflict-free LDS.128 (lane stride = 17 quads)
+constexpr int WARP_TILE = 32 * LANE_SPAN;    // 8704 B
+constexpr int SIMPLE_SPAN = 1024;            // cross-check kernel: bytes per thread
+
+struct ScanArgs {
+    const uint8_t *base;
+    const uint64_t *off;         // [n]
+    const uint64_t *len;         // [n]
+    const uint64_t *tile_first;  // [n+1] exclusive prefix of per-stream tile counts
+    uint32_t n_streams;
+    uint64_t total_tiles;
+    uint32_t mask, break_min;
+    const uint32_t *table;       // [256] device
+    uint64_t *cand;              // candidate keys
+    uint64_t cand_cap;
+    unsigned long long *cand_count;
+};
+cudaError_t launch_scan_simple(const ScanArgs &a, cudaStream_t st);
+cudaError_t launch_scan_tuned(const ScanArgs &a, const uint32_t *rot_table /*[256][64]*/, int sm_count, cudaStream_t st);
+cudaError_t launch_build_rot_table(const uint32_t *table, uint32_t *rot_table, cudaStream_t st);
+size_t scan_tuned_smem_bytes();
+
+// ---- resolve (K2) --------------------------------------------------------------
+struct ResolveArgs {
+    const uint64_t *keys_sorted;           // sorted candidate keys (KEY_SENTINEL padded)
+    const unsigned long long *cand_count;  // device
+    uint64_t cand_cap;
+    const uint64_t *len;                   // [n]
+    uint32_t n_streams;
+    uint32_t cmin, cmax;
+    int eof;                               // 1: emit final short chunk
+    uint32_t *counts;                      // [n] chunks per stream
+    uint64_t *chunk_first;                 // [n+1]
+    ChunkRef *chunks;                      // [chunk_cap]
+    uint64_t chunk_cap;
+    uint64_t *consumed;                    // [n] bytes covered by emitted chunks (eof==0)
+    unsigned long long *n_chunks;          // device total
+};
+cudaError_t launch_resolve(const ResolveArgs &a, cudaStream_t st);   // count + scan + write (3 launches)
+
+// ---- SHA-256 (K3) ----------------------------------------------------------------
+struct ShaArgs {
+    const uint8_t *base;
+    const uint64_t *off;                 // [n_streams] stream offsets (NULL: chunks[].start is absolute)
+    const ChunkRef *chunks;
+    const uint32_t *order;               // processing order (longest first) or NULL
+    const unsigned long long *n_chunks;  // device count
+    uint64_t chunk_cap;                  // launch bound
+    uint8_t *digests;                    // [chunk_cap][32], indexed by chunk id
+};
+cudaError_t launch_sha_simple(const ShaArgs &a, cudaStream_t st);
+cudaError_t launch_sha_tuned(const ShaArgs &a, int sm_count, cudaStream_t st);
+cudaError_t launch_len_keys(const ChunkRef *chunks, const unsigned long long *n_chunks, uint64_t cap,
+                            uint32_t *keys, uint32_t *vals, cudaStream_t st);
+cudaError_t launch_pack_chunks(const ChunkRef *chunks, const uint8_t *digests, const uint8_t *hit,
+                               const unsigned long long *n_chunks, uint64_t cap, pbsgpu_chunk *out, cudaStream_t st);
+
+// ---- digest set (K4) ----------------------------------------------------------------
+struct SetTable {
+    uint64_t *tags;     // [cap] 0 = empty
+    uint64_t *keys;     // [cap][4]
+    uint64_t cap;       // power of two
+};
+cudaError_t launch_set_make_keys(const uint8_t *d32, uint64_t n, uint64_t *tag, uint32_t *idx, cudaStream_t st);
+cudaError_t launch_set_mark_probe_insert(SetTable t, const uint8_t *d32, const uint64_t *tag_sorted,
+                                         const uint32_t *idx_sorted, uint64_t n, int do_insert, uint8_t *hit,
+                                         uint8_t *is_rep_miss, unsigned long long *n_new, cudaStream_t st);
+cudaError_t launch_set_rehash(SetTable from, SetTable to, cudaStream_t st);
+
+// ---- corpus (K5) ------------------------------------------------------------------
+cudaError_t launch_corpus_fill(const pbsgpu_corpus &c, uint64_t first_file, uint32_t n_files, uint8_t *dst,
+                               uint64_t stride, cudaStream_t st);
+
+}  // namespace pbsgpu

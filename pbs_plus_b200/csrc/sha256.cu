@@ -1,0 +1,190 @@
+// pbs_plus_b200/csrc/sha256.cu -- K3: batched per-chunk SHA-256 (FIPS 180-4), sm_100a.
+//
+// Replaces the per-chunk digest the reference's dedup writer computes for every chunk
+// cut inside transfer.ArchiveWriter.WriteEntryReader (reference
+// internal/pxarmount/commit.go:720, :858; CryptModeNone commit.go:314 => plain SHA-256
+// of the raw chunk bytes; Go crypto/sha256 in the reference build).
+//
+// SHA-256 is a serial chain per message, so the parallelism is ACROSS chunks: one lane
+// per chunk, chunks taken longest-first (K2's chunks sorted by length) so that the 32
+// lanes of a warp retire together and the longest chunks start first.  Integer work on
+// the ALU/FMA pipes; no tensor cores.  The kernel is instruction bound (~22 integer
+// ops per byte), not HBM bound -- see DESIGN.md for the ceiling this implies.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "internal.cuh"
+
+namespace pbsgpu {
+
+__constant__ uint32_t K256[64] = {
+    0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5,
+    0xd807aa98, 0x12835b01, 0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174,
+    0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da,
+    0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967,
+    0x27b70a85, 0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85,
+    0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070,
+    0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3,
+    0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
+
+// compile-time copy so that fully unrolled rounds take K as an immediate operand
+#define K256_LIST                                                                                          \
+    0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5,        \
+    0xd807aa98, 0x12835b01, 0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174,        \
+    0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da,        \
+    0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967,        \
+    0x27b70a85, 0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85,        \
+    0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070,        \
+    0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3,        \
+    0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2
+
+__device__ __forceinline__ uint32_t rotr(uint32_t x, int r) { return __funnelshift_r(x, x, r); }
+
+struct Sha256State { uint32_t h[8]; };
+
+__device__ __forceinline__ void sha_init(Sha256State &s) {
+    s.h[0] = 0x6a09e667; s.h[1] = 0xbb67ae85; s.h[2] = 0x3c6ef372; s.h[3] = 0xa54ff53a;
+    s.h[4] = 0x510e527f; s.h[5] = 0x9b05688c; s.h[6] = 0x1f83d9ab; s.h[7] = 0x5be0cd19;
+}
+
+// One compression: w[16] = big-endian message words (clobbered).
+__device__ __forceinline__ void sha_compress(Sha256State &s, uint32_t (&w)[16]) {
+    constexpr uint32_t K[64] = {K256_LIST};
+    uint32_t a = s.h[0], b = s.h[1], c = s.h[2], d = s.h[3], e = s.h[4], f = s.h[5], g = s.h[6], h = s.h[7];
+#pragma unroll
+    for (int i = 0; i < 64; i++) {
+        if (i >= 16) {
+            uint32_t w15 = w[(i + 1) & 15], w2 = w[(i + 14) & 15];
+            uint32_t s0 = rotr(w15, 7) ^ rotr(w15, 18) ^ (w15 >> 3);
+            uint32_t s1 = rotr(w2, 17) ^ rotr(w2, 19) ^ (w2 >> 10);
+            w[i & 15] = w[i & 15] + s0 + w[(i + 9) & 15] + s1;
+        }
+        uint32_t S1 = rotr(e, 6) ^ rotr(e, 11) ^ rotr(e, 25);
+        uint32_t ch = (e & f) ^ (~e & g);
+        uint32_t t1 = h + S1 + ch + K[i] + w[i & 15];
+        uint32_t S0 = rotr(a, 2) ^ rotr(a, 13) ^ rotr(a, 22);
+        uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
+        uint32_t t2 = S0 + mj;
+        h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+    }
+    s.h[0] += a; s.h[1] += b; s.h[2] += c; s.h[3] += d; s.h[4] += e; s.h[5] += f; s.h[6] += g; s.h[7] += h;
+}
+
+// Padding blocks for a message of `len` bytes whose unprocessed tail (rem = len % 64
+// bytes) starts at `tail`.
+__device__ __noinline__ void sha_finish(Sha256State &s, const uint8_t *tail, uint32_t rem, uint64_t len, uint8_t *out) {
+    const uint64_t bits = len * 8;
+    const int nblk = rem < 56 ? 1 : 2;
+    for (int blk = 0; blk < nblk; blk++) {
+        uint32_t w[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                uint32_t idx = blk * 64 + i * 4 + k;
+                uint32_t byte = idx < rem ? tail[idx] : (idx == rem ? 0x80u : 0u);
+                v = (v << 8) | byte;
+            }
+            w[i] = v;
+        }
+        if (blk == nblk - 1) { w[14] = (uint32_t)(bits >> 32); w[15] = (uint32_t)bits; }
+        sha_compress(s, w);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        out[4 * i] = (uint8_t)(s.h[i] >> 24); out[4 * i + 1] = (uint8_t)(s.h[i] >> 16);
+        out[4 * i + 2] = (uint8_t)(s.h[i] >> 8); out[4 * i + 3] = (uint8_t)s.h[i];
+    }
+}
+
+// 64 message bytes at arbitrary alignment -> 16 big-endian words.
+// Loads 4-byte aligned words; ONE PRMT per word does the realignment and the byte swap.
+__device__ __forceinline__ void load_block_be(const uint8_t *p, uint32_t (&w)[16]) {
+    const uint32_t sh = (uint32_t)((uintptr_t)p & 3);
+    const uint32_t *q = (const uint32_t *)(p - sh);
+    // bytes of {lo,hi} are indexed 0..7; big-endian word = bytes sh, sh+1, sh+2, sh+3
+    const uint32_t sel = (sh + 3) | ((sh + 2) << 4) | ((sh + 1) << 8) | (sh << 12);
+    uint32_t x[17];
+#pragma unroll
+    for (int i = 0; i < 16; i++) x[i] = __ldg(q + i);
+    x[16] = sh ? __ldg(q + 16) : 0;   // never touch the word past the block when aligned
+#pragma unroll
+    for (int i = 0; i < 16; i++) w[i] = __byte_perm(x[i], x[i + 1], sel);
+}
+
+// ---------------------------------------------------------------------------
+// Cross-check / v0 kernel: one thread per chunk, chunks in `order` (longest first).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(64) k_sha_simple(ShaArgs a) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long n = *a.n_chunks;
+    if (n > a.chunk_cap) n = a.chunk_cap;
+    if (t >= n) return;
+    uint32_t id = a.order ? a.order[t] : (uint32_t)t;
+    ChunkRef c = a.chunks[id];
+    const uint8_t *p = a.base + (a.off ? a.off[c.stream] : 0) + c.start;
+    Sha256State s;
+    sha_init(s);
+    uint32_t nblk = c.len >> 6;
+    for (uint32_t b = 0; b < nblk; b++) {
+        uint32_t w[16];
+        load_block_be(p + (uint64_t)b * 64, w);
+        sha_compress(s, w);
+    }
+    sha_finish(s, p + (uint64_t)nblk * 64, c.len & 63, c.len, a.digests + (uint64_t)id * 32);
+}
+
+cudaError_t launch_sha_simple(const ShaArgs &a, cudaStream_t st) {
+    if (a.chunk_cap == 0) return cudaSuccess;
+    uint64_t blocks = (a.chunk_cap + 63) / 64;
+    k_sha_simple<<<(unsigned)blocks, 64, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sha_tuned(const ShaArgs &a, int sm_count, cudaStream_t st) {
+    (void)sm_count;
+    return launch_sha_simple(a, st);   // replaced by the tuned kernel below once measured
+}
+
+// keys for the longest-first ordering: key = len (sorted descending), val = chunk id.
+// Entries past n_chunks get key 0 so they sort last.
+__global__ void k_len_keys(const ChunkRef *chunks, const unsigned long long *n_chunks, uint64_t cap, uint32_t *keys,
+                           uint32_t *vals) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cap) return;
+    unsigned long long n = *n_chunks;
+    keys[i] = i < n ? chunks[i].len : 0u;
+    vals[i] = (uint32_t)i;
+}
+cudaError_t launch_len_keys(const ChunkRef *chunks, const unsigned long long *n_chunks, uint64_t cap, uint32_t *keys,
+                            uint32_t *vals, cudaStream_t st) {
+    if (cap == 0) return cudaSuccess;
+    k_len_keys<<<(unsigned)((cap + 255) / 256), 256, 0, st>>>(chunks, n_chunks, cap, keys, vals);
+    return cudaGetLastError();
+}
+
+// (stream, end_off, digest, flags) records in (stream, chunk) order for the caller
+__global__ void k_pack_chunks(const ChunkRef *chunks, const uint8_t *digests, const uint8_t *hit,
+                              const unsigned long long *n_chunks, uint64_t cap, pbsgpu_chunk *out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long n = *n_chunks;
+    if (n > cap) n = cap;
+    if (i >= n) return;
+    ChunkRef c = chunks[i];
+    // pbsgpu_chunk = 6 x u64: {stream|flags<<32, end_off, digest[4]}
+    uint64_t *o = (uint64_t *)(out + i);
+    const uint64_t *d = (const uint64_t *)(digests + i * 32);
+    uint32_t flags = (hit && hit[i]) ? PBSGPU_CHUNK_KNOWN : 0u;
+    o[0] = (uint64_t)c.stream | ((uint64_t)flags << 32);
+    o[1] = c.start + c.len;
+    o[2] = d[0]; o[3] = d[1]; o[4] = d[2]; o[5] = d[3];
+}
+cudaError_t launch_pack_chunks(const ChunkRef *chunks, const uint8_t *digests, const uint8_t *hit,
+                               const unsigned long long *n_chunks, uint64_t cap, pbsgpu_chunk *out, cudaStream_t st) {
+    if (cap == 0) return cudaSuccess;
+    k_pack_chunks<<<(unsigned)((cap + 255) / 256), 256, 0, st>>>(chunks, digests, hit, n_chunks, cap, out);
+    return cudaGetLastError();
+}
+
+}  // namespace pbsgpu

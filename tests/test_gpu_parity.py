@@ -1,0 +1,386 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle.
+
+Oracle = restatement (oracle/oracle.c); boundaries are bit-exact against IT
+("parity unpinned" against the absent Go module); digests additionally against hashlib.
+"""
+import hashlib
+import json
+import os
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle
+import pbs_plus_b200 as pg
+
+pytestmark = pytest.mark.gpu
+GOLDEN = Path(__file__).parent / "golden"
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch as t
+    return t
+
+
+@pytest.fixture(scope="module")
+def eng():
+    e = pg.Engine(0)
+    yield e
+    e.close()
+
+
+def rnd(n, seed):
+    return np.random.default_rng(seed).integers(0, 256, size=n, dtype=np.uint8)
+
+
+def to_dev(torch, a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def pack(arrs, align=256, lead=0):
+    """Pack host arrays into one buffer; returns (buf, off, len)."""
+    offs, pos = [], lead
+    for a in arrs:
+        offs.append(pos)
+        pos += (len(a) + align - 1) // align * align if align > 1 else len(a)
+    buf = np.zeros(max(pos, 1) + 64, dtype=np.uint8)
+    for a, o in zip(arrs, offs):
+        buf[o:o + len(a)] = a
+    return buf, np.array(offs, dtype=np.uint64), np.array([len(a) for a in arrs], dtype=np.uint64)
+
+
+def oracle_ends(cfg_o, arrs):
+    ends, first = [], [0]
+    for a in arrs:
+        e = oracle.chunk_ends(cfg_o, a).tolist()
+        ends += e
+        first.append(len(ends))
+    return ends, first
+
+
+RAGGED = [0, 1, 63, 64, 65, 100, 255, 256, 257, 1023, 1024, 1025, 4095, 8703, 8704, 8705, 8704 * 2 - 1, 8704 * 2,
+          8704 * 2 + 1, 8704 * 3 + 17, 50_000, 123_457]
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("avg", [256, 1024, 4096])
+def test_scan_ragged_streams_match_oracle(eng, torch, variant, avg):
+    eng.set_kernel_variant(variant)
+    try:
+        arrs = [rnd(n, 100 + i) for i, n in enumerate(RAGGED)]
+        buf, off, ln = pack(arrs)
+        ends, first = eng.scan_batch(pg.make_config(avg), to_dev(torch, buf), off, ln)
+        ref_e, ref_f = oracle_ends(oracle.config(avg), arrs)
+        assert ends.tolist() == ref_e and first.tolist() == ref_f
+    finally:
+        eng.set_kernel_variant(0)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_scan_unaligned_offsets(eng, torch, variant):
+    """Stream starts at every residue mod 16 (TMA needs 16 B; the kernel must cope)."""
+    eng.set_kernel_variant(variant)
+    try:
+        arrs = [rnd(30_000 + 7 * i, 200 + i) for i in range(17)]
+        buf, off, ln = pack(arrs, align=1, lead=1)
+        assert len({int(o) % 16 for o in off}) > 8
+        ends, first = eng.scan_batch(pg.make_config(1024), to_dev(torch, buf), off, ln)
+        ref_e, ref_f = oracle_ends(oracle.config(1024), arrs)
+        assert ends.tolist() == ref_e and first.tolist() == ref_f
+    finally:
+        eng.set_kernel_variant(0)
+
+
+def test_scan_large_random_stream_all_restatements(eng, torch):
+    data = rnd(32 << 20, 7)
+    for avg in (4096, 65536, 1 << 20):
+        ends, _ = eng.scan_batch(pg.make_config(avg), to_dev(torch, data), [0], [len(data)])
+        assert ends.tolist() == oracle.chunk_ends(oracle.config(avg), data).tolist()
+
+
+def test_forced_cuts_on_constant_data(eng, torch):
+    data = np.zeros(1_000_000, dtype=np.uint8)
+    ends, _ = eng.scan_batch(pg.make_config(1024), to_dev(torch, data), [0], [len(data)])
+    assert ends.tolist() == list(range(4096, 1_000_000, 4096)) + [1_000_000]
+
+
+def test_dense_candidates_overflow_rerun_is_exact(eng, torch):
+    """A table that makes ~50 % of positions candidates overflows the statistically
+    sized candidate buffer; the library reruns with a larger one and stays exact."""
+    t = np.zeros(256, dtype=np.uint32)
+    t[0] = 0xFFFFFFFF
+    data = np.random.default_rng(3).integers(0, 2, size=600_000, dtype=np.uint8)
+    ends, _ = eng.scan_batch(pg.make_config(512, t), to_dev(torch, data), [0], [len(data)])
+    assert ends.tolist() == oracle.chunk_ends(oracle.config(512, t), data).tolist()
+
+
+def test_custom_table(eng, torch):
+    t = np.random.default_rng(9).integers(0, 2**32, size=256, dtype=np.uint32)
+    data = rnd(2_000_000, 11)
+    ends, _ = eng.scan_batch(pg.make_config(2048, t), to_dev(torch, data), [0], [len(data)])
+    assert ends.tolist() == oracle.chunk_ends(oracle.config(2048, t), data).tolist()
+    ends2, _ = eng.scan_batch(pg.make_config(2048), to_dev(torch, data), [0], [len(data)])   # table switch back
+    assert ends2.tolist() == oracle.chunk_ends(oracle.config(2048), data).tolist()
+
+
+def test_sha256_batch_all_small_lengths_and_alignments(eng, torch):
+    data = rnd(70_000, 21)
+    offs, lens = [], []
+    for n in list(range(0, 200)) + [255, 256, 257, 1000, 4096, 65_535]:
+        for a in (0, 1, 2, 3, 5, 13):
+            offs.append(a + 7 * (n % 11))
+            lens.append(n)
+    for host in (False, True):
+        dig = eng.sha256_batch(data if host else to_dev(torch, data), offs, lens)
+        for o, n, d in zip(offs, lens, dig):
+            assert bytes(d) == hashlib.sha256(data[o:o + n].tobytes()).digest(), (o, n, host)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_chunk_digest_batch_matches_oracle(eng, torch, variant):
+    eng.set_kernel_variant(variant)
+    try:
+        arrs = [rnd(n, 300 + i) for i, n in enumerate([0, 5, 70_000, 1, 333_333, 64, 1 << 20])]
+        buf, off, ln = pack(arrs, align=1, lead=3)
+        for avg in (256, 4096):
+            rec = eng.chunk_digest_batch(pg.make_config(avg), to_dev(torch, buf), off, ln)
+            ref = oracle.chunk_digest_streams(oracle.config(avg), arrs, threads=4)
+            assert rec.tobytes() == ref.tobytes()
+    finally:
+        eng.set_kernel_variant(0)
+
+
+def test_golden_vectors_through_the_c_abi(eng, torch):
+    for ln in (GOLDEN / "chunks_oracle.jsonl").read_text().splitlines():
+        g = json.loads(ln)
+        c = pg.corpus(seed=g["seed"], file_len=g["len"], block_len=g["block_len"])
+        stride = (g["len"] + 255) // 256 * 256
+        dev = torch.zeros(stride * (g["file_id"] + 1), dtype=torch.uint8, device="cuda")
+        eng.corpus_fill(c, 0, g["file_id"] + 1, dev, stride)
+        rec = eng.chunk_digest_batch(pg.make_config(g["avg"]), dev, [g["file_id"] * stride], [g["len"]])
+        assert rec["end_off"].tolist() == g["cuts"]
+        assert [bytes(x).hex() for x in rec["digest"]] == g["digests"]
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(dup_permille=300, run_blocks=2), dict(edit_mode=1),
+                                dict(edit_mode=2, dup_permille=300, run_blocks=3)])
+def test_device_corpus_equals_oracle_corpus(eng, torch, kw):
+    for file_len, block_len in ((1 << 16, 1 << 12), (100_003, 4096), (7, 8), (8192, 8192)):
+        co = oracle.corpus(seed=2, file_len=file_len, block_len=block_len, **kw)
+        cg = pg.corpus(seed=2, file_len=file_len, block_len=block_len, **kw)
+        stride = (file_len + 255) // 256 * 256
+        dev = torch.zeros(stride * 5, dtype=torch.uint8, device="cuda")
+        eng.corpus_fill(cg, 3, 5, dev, stride)
+        host = dev.cpu().numpy().reshape(5, stride)
+        for i in range(5):
+            assert (host[i, :file_len] == oracle.corpus_file(co, 3 + i)).all(), (kw, file_len, i)
+
+
+def test_cfg2_shape_scaled_parity_and_invariants(eng, torch):
+    """BASELINE cfg2 shape (N x 64 MiB files, 4 MiB average) scaled to 12 files: cut-for-cut and
+    digest-for-digest against the oracle; plus the size-independent invariants."""
+    n_files, file_len = 12, 64 << 20
+    cg = pg.corpus(seed=2, file_len=file_len)
+    dev = torch.empty(n_files * file_len, dtype=torch.uint8, device="cuda")
+    eng.corpus_fill(cg, 0, n_files, dev, file_len)
+    off = np.arange(n_files, dtype=np.uint64) * file_len
+    ln = np.full(n_files, file_len, dtype=np.uint64)
+    cfg = pg.buzhash.NewConfig(4096)
+    rec = eng.chunk_digest_batch(cfg, dev, off, ln)
+    files = oracle.corpus_files(oracle.corpus(seed=2, file_len=file_len), 0, n_files)
+    ref = oracle.chunk_digest_streams(oracle.config(4 << 20), files, threads=os.cpu_count())
+    assert rec.tobytes() == ref.tobytes()
+    for s in range(n_files):
+        e = np.concatenate([[0], rec[rec["stream"] == s]["end_off"]]).astype(np.int64)
+        lens = np.diff(e)
+        assert e[-1] == file_len and (lens[:-1] >= cfg.min).all() and (lens <= cfg.max).all()
+
+
+def test_incremental_edits_resynchronise_like_the_oracle(eng, torch):
+    """BASELINE cfg5: same corpus with ~1 % byte edits (uniform) and with one edited byte in ~1 % of
+    blocks (clustered): boundaries shift exactly as the oracle's do, and away from the edits
+    the chunks (digests) are unchanged."""
+    n_files, file_len, bl = 6, 8 << 20, 1 << 16
+    cfg_g, cfg_o = pg.make_config(1 << 16), oracle.config(1 << 16)
+    off = np.arange(n_files, dtype=np.uint64) * file_len
+    ln = np.full(n_files, file_len, dtype=np.uint64)
+    results = {}
+    for mode in (0, 1, 2):
+        cg = pg.corpus(seed=5, file_len=file_len, block_len=bl, edit_mode=mode)
+        dev = torch.empty(n_files * file_len, dtype=torch.uint8, device="cuda")
+        eng.corpus_fill(cg, 0, n_files, dev, file_len)
+        rec = eng.chunk_digest_batch(cfg_g, dev, off, ln)
+        files = oracle.corpus_files(oracle.corpus(seed=5, file_len=file_len, block_len=bl, edit_mode=mode), 0, n_files)
+        assert rec.tobytes() == oracle.chunk_digest_streams(cfg_o, files, threads=4).tobytes(), mode
+        results[mode] = {bytes(d) for d in rec["digest"]}
+    assert len(results[0] & results[2]) > 0.5 * len(results[0])      # clustered edits: most chunks survive
+    assert len(results[0] & results[1]) < 0.05 * len(results[0])     # uniform 1 % edits: nothing survives
+
+
+def test_async_jobs_overlap_and_match_sync(eng, torch):
+    cfg = pg.make_config(1 << 16)
+    devs, jobs = [], []
+    for k in range(5):
+        data = rnd(6 << 20, 400 + k)
+        d = to_dev(torch, data)
+        devs.append((d, data))
+        jobs.append(eng.submit(cfg, d, [0, 3 << 20], [3 << 20, 3 << 20]))
+    for (d, data), j in zip(devs, jobs):
+        rec, timing = j.wait()
+        ref = oracle.chunk_digest_streams(oracle.config(1 << 16), [data[:3 << 20], data[3 << 20:]])
+        assert rec.tobytes() == ref.tobytes() and timing["chunks"] == len(ref)
+
+
+def test_host_input_is_staged_in_groups(torch):
+    os.environ["PBSGPU_STAGE_BYTES"] = str(1 << 20)      # force several staging groups
+    try:
+        e = pg.Engine(0)
+    finally:
+        del os.environ["PBSGPU_STAGE_BYTES"]
+    try:
+        arrs = [rnd(n, 500 + i) for i, n in enumerate([400_000, 0, 900_000, 1_500_000, 10, 700_000, 333])]
+        rec = e.chunk_digest_streams(pg.make_config(4096), arrs)
+        assert rec.tobytes() == oracle.chunk_digest_streams(oracle.config(4096), arrs).tobytes()
+        pinned = e.host_alloc(2_000_000)                 # C-owned pinned staging, as the Go side would use
+        pinned[:] = rnd(2_000_000, 77)
+        rec = e.chunk_digest_batch(pg.make_config(4096), pinned, [0, 1_000_000], [1_000_000, 1_000_000])
+        ref = oracle.chunk_digest_streams(oracle.config(4096), [np.array(pinned[:1_000_000]), np.array(pinned[1_000_000:])])
+        assert rec.tobytes() == ref.tobytes()
+        e.host_free(pinned)
+    finally:
+        e.close()
+
+
+def test_output_capacity_error_reports_needed(eng, torch):
+    import ctypes as C
+    data = rnd(100_000, 1)
+    cfg = pg.make_config(256)
+    off = np.array([0], dtype=np.uint64); ln = np.array([len(data)], dtype=np.uint64)
+    out = np.zeros(3, dtype=pg.CHUNK_DTYPE); n_out = C.c_uint64()
+    d = to_dev(torch, data)
+    rc = eng._L.pbsgpu_chunk_digest_batch(eng._h, C.byref(cfg), d.data_ptr(), off.ctypes.data, ln.ctypes.data, 1, None,
+                                          out.ctypes.data, 3, C.byref(n_out))
+    assert rc == -34 and n_out.value == len(oracle.chunk_ends(oracle.config(256), data))
+    assert b"capacity" in eng._L.pbsgpu_strerror(eng._h)
+
+
+# ---- a4: digest set ---------------------------------------------------------------
+def test_digest_set_matches_oracle_set(eng):
+    rng = np.random.default_rng(12)
+    s_g, s_o = eng.digest_set(16), oracle.DigestSet(16)
+    pool = rng.integers(0, 256, size=(5000, 32), dtype=np.uint8)
+    for rnd_i in range(6):                                # growth + rehash happen along the way
+        idx = rng.integers(0, 1000 * (rnd_i + 1), size=3000).clip(max=4999)
+        batch = pool[idx]
+        assert (s_g.insert(batch) == s_o.probe(batch, insert=True)).all()
+        assert len(s_g) == len(s_o)
+        probe = pool[rng.integers(0, 5000, size=2000)]
+        assert (s_g.probe(probe) == s_o.probe(probe, insert=False)).all()
+        assert len(s_g) == len(s_o)
+
+
+def test_digest_set_tag_collisions_and_identical_runs(eng):
+    """Digests that share their first 8 bytes (the table's tag) but differ later must stay
+    distinct; a run of identical digests (e.g. zero-filled files) is one entry."""
+    s = eng.digest_set(4)
+    d = np.zeros((300, 32), dtype=np.uint8)
+    d[:, :8] = 7                                          # identical tag
+    d[:100, 31] = np.arange(100)                          # 100 distinct digests
+    d[100:200, 31] = np.arange(100)                       # the same 100 again
+    d[200:, 31] = 5                                       # 100 copies of one of them
+    hit = s.insert(d)
+    assert hit[:100].sum() == 0 and hit[100:].all() and len(s) == 100
+    z = np.zeros((1, 32), dtype=np.uint8)                 # all-zero digest: tag 0 is remapped, still exact
+    assert s.insert(z)[0] == 0 and s.probe(z)[0] == 1 and len(s) == 101
+
+
+def test_batch_with_set_flags_known_chunks_in_order(eng, torch):
+    """30 %-duplicate corpus (BASELINE cfg3 shape, scaled): the KNOWN flags and the hit-rate equal
+    what the oracle computes in (file, chunk) order; a second pass over the same data is 100 % known."""
+    n_files, file_len, bl = 24, 4 << 20, 1 << 16
+    kw = dict(seed=3, file_len=file_len, block_len=bl, run_blocks=8, dup_permille=300)
+    dev = torch.empty(n_files * file_len, dtype=torch.uint8, device="cuda")
+    eng.corpus_fill(pg.corpus(**kw), 0, n_files, dev, file_len)
+    off = np.arange(n_files, dtype=np.uint64) * file_len
+    ln = np.full(n_files, file_len, dtype=np.uint64)
+    s = eng.digest_set()
+    rec = eng.chunk_digest_batch(pg.make_config(1 << 14), dev, off, ln, s)
+    files = oracle.corpus_files(oracle.corpus(**kw), 0, n_files)
+    ref = oracle.chunk_digest_streams(oracle.config(1 << 14), files, threads=4)
+    so = oracle.DigestSet()
+    ref["flags"] = so.probe(ref["digest"], insert=True)
+    assert rec.tobytes() == ref.tobytes()
+    hit_rate = (rec["flags"] & 1).mean()
+    assert 0.15 < hit_rate < 0.40, hit_rate
+    rec2 = eng.chunk_digest_batch(pg.make_config(1 << 14), dev, off, ln, s)
+    assert (rec2["flags"] & 1).all() and len(s) == len(so)
+
+
+def test_seed_from_previous_dynamic_index(eng, torch):
+    data = rnd(3_000_000, 31)
+    cfg = pg.make_config(1 << 14)
+    rec = eng.chunk_digest_batch(cfg, to_dev(torch, data), [0], [len(data)])
+    didx = bytearray(4096)                                           # header (magic/uuid/ctime/csum: not read)
+    for r in rec[: len(rec) // 2]:                                   # previous snapshot held the first half
+        didx += int(r["end_off"]).to_bytes(8, "little") + bytes(r["digest"])
+    s = eng.digest_set()
+    assert s.seed_didx(bytes(didx)) == len(rec) // 2
+    rec2 = eng.chunk_digest_batch(cfg, to_dev(torch, data), [0], [len(data)], s)
+    assert (rec2["flags"][: len(rec) // 2] & 1).all() and not (rec2["flags"][len(rec) // 2:] & 1).any()
+    with pytest.raises(pg.PbsGpuError):
+        s.seed_didx(b"\0" * 4097)
+
+
+# ---- streaming form ---------------------------------------------------------------------
+@pytest.mark.parametrize("window", [4096, 20_000, 1 << 20])
+def test_streaming_is_split_invariant(torch, window):
+    os.environ["PBSGPU_STREAM_WINDOW"] = str(window)
+    e = pg.Engine(0)
+    try:
+        data = rnd(700_001, 41)
+        ref = oracle.chunk_digest(oracle.config(1024), data)
+        for pieces in ([len(data)], [1, 63, 64, 1000, 99_999, 10**9], [7777] * 200):
+            st = e.stream(pg.make_config(1024))
+            pos, got = 0, []
+            for p in pieces:
+                if pos >= len(data):
+                    break
+                st.write(data[pos:pos + p]); pos += p
+                got.append(st.poll())
+            got.append(st.finish())
+            rec = np.concatenate(got)
+            assert rec.tobytes() == ref.tobytes(), (window, pieces[:3])
+            with pytest.raises(pg.PbsGpuError):
+                st.write(b"x")
+            st.close()
+        st = e.stream(pg.make_config(1024))                          # empty stream: no chunks
+        assert len(st.finish()) == 0
+    finally:
+        del os.environ["PBSGPU_STREAM_WINDOW"]
+        e.close()
+
+
+# ---- reference-facing mirror -----------------------------------------------------------
+def test_dedup_writer_mirror_of_the_reference_surface(eng):
+    import io
+    cfg = pg.buzhash.NewConfigBytes(4096)
+    uploaded = {}
+    w = pg.transfer.NewRemoteDedupSplitArchiveWriter(eng, cfg, known=eng.digest_set(),
+                                                     upload=lambda d, b: uploaded.__setitem__(d, b))
+    files = {"a.bin": rnd(200_000, 51), "b.bin": rnd(50_000, 52), "empty": rnd(0, 53)}
+    files["a-copy.bin"] = files["a.bin"].copy()
+    for name, data in files.items():
+        w.WriteEntryReader(pg.transfer.Entry(name, len(data)), io.BytesIO(data.tobytes()), len(data))
+    with pytest.raises(IOError):                                     # io.ReadFull semantics: short reader is an error
+        w.WriteEntryReader(pg.transfer.Entry("short", 10), io.BytesIO(b"abc"), 10)
+    index = w.Finish()
+    ref = oracle.chunk_digest_streams(oracle.config(4096), list(files.values()))
+    assert [(r.end_off, r.digest) for r in index] == [(int(r["end_off"]), bytes(r["digest"])) for r in ref]
+    known = [r.known for r in index]
+    n_a = sum(1 for r in index if r.path == "a.bin")
+    assert not any(known[:n_a]) and all(r.known for r in index if r.path == "a-copy.bin")
+    for d, b in uploaded.items():
+        assert hashlib.sha256(b).digest() == d
+    assert len(uploaded) == len({r.digest for r in index})
