@@ -1,0 +1,180 @@
+//go:build gpu && cgo
+
+// Package gpuchunk is the cgo shim a pbs-plus maintainer adds to call libpbsgpu.so
+// (include/pbsgpu.h) from the Go host code.  It is the reference-side binding for the
+// ONE hot path this repository accelerates: buzhash boundary scan + per-chunk SHA-256 +
+// known-digest probe, i.e. what happens inside
+//
+//	writer.WriteEntryReader(entry, tee, size)          internal/pxarmount/commit.go:720, :858
+//
+// configured by buzhash.NewConfig(4096) (commit.go:302-305) and seeded from the previous
+// snapshot's index (commit.go:286-294, :324-329).
+//
+// NOT COMPILED IN THIS REPOSITORY'S CI: the build image has no Go toolchain (SURVEY.md
+// section 0).  The same C symbols are exercised by the Python ctypes tests (tests/) and the
+// C++ driver (tests/cxx/).  pxar-mount is built CGO_ENABLED=0 today (.goreleaser.yaml:56);
+// this file only builds with `-tags gpu` and CGO_ENABLED=1.
+package gpuchunk
+
+/*
+#cgo CFLAGS: -I${SRCDIR}/../../include
+#cgo LDFLAGS: -L${SRCDIR}/../../pbs_plus_b200 -lpbsgpu -Wl,-rpath,${SRCDIR}/../../pbs_plus_b200
+#include <stdlib.h>
+#include "pbsgpu.h"
+*/
+import "C"
+
+import (
+	"errors"
+	"fmt"
+	"io"
+	"runtime"
+	"unsafe"
+)
+
+// Config mirrors buzhash.Config (opaque in the reference; built by NewConfig).
+type Config struct{ c C.pbsgpu_cfg }
+
+// NewConfig mirrors buzhash.NewConfig(avgKiB) (commit.go:303 passes 4096 = 4 MiB).
+func NewConfig(avgKiB int) (Config, error) {
+	var cfg Config
+	if rc := C.pbsgpu_config_kib(C.uint32_t(avgKiB), nil, &cfg.c); rc != 0 {
+		return cfg, fmt.Errorf("buzhash: invalid average chunk size %d KiB (rc %d)", avgKiB, int(rc))
+	}
+	return cfg, nil
+}
+
+// Engine is one GPU context.  Safe to use from any goroutine: the C side binds the device
+// per call and serialises calls per context (no thread-local CUDA state).
+type Engine struct{ ctx *C.pbsgpu_ctx }
+
+func Open(device int) (*Engine, error) {
+	var ctx *C.pbsgpu_ctx
+	if rc := C.pbsgpu_open(C.int(device), &ctx); rc != 0 {
+		return nil, fmt.Errorf("pbsgpu_open(%d): rc %d (no CUDA device; there is no CPU fallback)", device, int(rc))
+	}
+	e := &Engine{ctx}
+	runtime.SetFinalizer(e, func(e *Engine) { e.Close() })
+	return e, nil
+}
+
+func (e *Engine) Close() {
+	if e.ctx != nil {
+		C.pbsgpu_close(e.ctx)
+		e.ctx = nil
+	}
+}
+
+func (e *Engine) err(rc C.int) error {
+	if rc == 0 {
+		return nil
+	}
+	return fmt.Errorf("pbsgpu: %s (rc %d)", C.GoString(C.pbsgpu_strerror(e.ctx)), int(rc))
+}
+
+// KnownSet mirrors the session's known-chunk bookkeeping (PreviousBackupRef, commit.go:286-294).
+type KnownSet struct {
+	e *Engine
+	s *C.pbsgpu_set
+}
+
+func (e *Engine) NewKnownSet(capacityHint uint64) (*KnownSet, error) {
+	var s *C.pbsgpu_set
+	if err := e.err(C.pbsgpu_set_create(e.ctx, C.uint64_t(capacityHint), &s)); err != nil {
+		return nil, err
+	}
+	return &KnownSet{e, s}, nil
+}
+
+// SeedFromDidx feeds the bytes of the previous .ppxar.didx (origPayloadIdx, commit.go:324-328).
+func (k *KnownSet) SeedFromDidx(didx []byte) (uint64, error) {
+	if len(didx) == 0 {
+		return 0, nil
+	}
+	var n C.uint64_t
+	rc := C.pbsgpu_set_seed_didx(k.s, (*C.uint8_t)(unsafe.Pointer(&didx[0])), C.uint64_t(len(didx)), &n)
+	return uint64(n), k.e.err(rc)
+}
+
+func (k *KnownSet) Close() { C.pbsgpu_set_destroy(k.s) }
+
+// Chunk is one dynamic-index entry: (end offset, digest) + whether the digest was known.
+type Chunk struct {
+	Stream uint32
+	Known  bool
+	End    uint64
+	Digest [32]byte
+}
+
+// Batch accumulates whole files in C-owned PINNED staging (Go pointers are never retained by C)
+// and pushes them through the GPU in one call -- the batched form of the per-file loop at
+// commit.go:604-625 / :697-731.
+type Batch struct {
+	e    *Engine
+	cfg  Config
+	buf  unsafe.Pointer
+	cap  uint64
+	fill uint64
+	off  []C.uint64_t
+	ln   []C.uint64_t
+}
+
+func (e *Engine) NewBatch(cfg Config, stagingBytes uint64) (*Batch, error) {
+	p := C.pbsgpu_host_alloc(e.ctx, C.uint64_t(stagingBytes))
+	if p == nil {
+		return nil, errors.New("pbsgpu: pinned staging allocation failed")
+	}
+	return &Batch{e: e, cfg: cfg, buf: p, cap: stagingBytes}, nil
+}
+
+// WriteEntryReader mirrors transfer.ArchiveWriter.WriteEntryReader(entry, reader, size): it pulls
+// exactly size bytes from r (io.ReadFull semantics) into the staging buffer.
+func (b *Batch) WriteEntryReader(r io.Reader, size uint64) error {
+	start := (b.fill + 255) &^ 255
+	if start+size > b.cap {
+		return errors.New("pbsgpu: staging full, call Flush first")
+	}
+	dst := unsafe.Slice((*byte)(unsafe.Add(b.buf, start)), size)
+	if _, err := io.ReadFull(r, dst); err != nil {
+		return fmt.Errorf("read payload: %w", err)
+	}
+	b.off = append(b.off, C.uint64_t(start))
+	b.ln = append(b.ln, C.uint64_t(size))
+	b.fill = start + size
+	return nil
+}
+
+// Flush runs scan -> cut -> SHA-256 -> probe for every queued file and returns the chunks in
+// (file, offset) order; Known chunks need no upload ("Only new chunks are uploaded").
+func (b *Batch) Flush(known *KnownSet) ([]Chunk, error) {
+	n := len(b.off)
+	if n == 0 {
+		return nil, nil
+	}
+	capChunks := uint64(n)
+	for _, l := range b.ln {
+		capChunks += uint64(l) / uint64(b.cfg.c.min)
+	}
+	out := make([]C.pbsgpu_chunk, capChunks+1)
+	var nOut C.uint64_t
+	var set *C.pbsgpu_set
+	if known != nil {
+		set = known.s
+	}
+	rc := C.pbsgpu_chunk_digest_batch(b.e.ctx, &b.cfg.c, b.buf, &b.off[0], &b.ln[0], C.uint32_t(n), set,
+		&out[0], C.uint64_t(len(out)), &nOut)
+	if err := b.e.err(rc); err != nil {
+		return nil, err
+	}
+	res := make([]Chunk, int(nOut))
+	for i := range res {
+		res[i].Stream = uint32(out[i].stream)
+		res[i].Known = out[i].flags&C.PBSGPU_CHUNK_KNOWN != 0
+		res[i].End = uint64(out[i].end_off)
+		copy(res[i].Digest[:], C.GoBytes(unsafe.Pointer(&out[i].digest[0]), 32))
+	}
+	b.off, b.ln, b.fill = b.off[:0], b.ln[:0], 0
+	return res, nil
+}
+
+func (b *Batch) Close() { C.pbsgpu_host_free(b.e.ctx, b.buf) }

@@ -158,7 +158,8 @@ void pbsgpu_stream_close(pbsgpu_stream *s);
 int pbsgpu_set_create(pbsgpu_ctx *ctx, uint64_t capacity_hint, pbsgpu_set **out);
 void pbsgpu_set_destroy(pbsgpu_set *set);
 /* d32: n*32 bytes, HOST or DEVICE pointer.  hit (HOST, n bytes, may be NULL):
- * 1 = already present before this call or earlier within it. */
+ * insert: 1 = already present before this call or earlier within it (then inserted);
+ * probe : 1 = present in the set (plain membership, nothing inserted). */
 int pbsgpu_set_insert(pbsgpu_set *set, const uint8_t *d32, uint64_t n, uint8_t *hit);
 int pbsgpu_set_probe(pbsgpu_set *set, const uint8_t *d32, uint64_t n, uint8_t *hit);
 int pbsgpu_set_count(pbsgpu_set *set, uint64_t *count);

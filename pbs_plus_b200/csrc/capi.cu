@@ -639,7 +639,7 @@ static int batch_host(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg, const uint8_t *bas
                       const uint64_t *len, uint32_t n, pbsgpu_chunk *out, uint64_t cap, uint64_t *n_out) {
     size_t fr = 0, tot = 0;
     CK(cudaMemGetInfo(&fr, &tot));
-    uint64_t stage = ctx->stage_bytes ? ctx->stage_bytes : std::min<uint64_t>(4ull << 30, fr / 8);
+    uint64_t stage = ctx->stage_bytes ? ctx->stage_bytes : std::min<uint64_t>(4ull << 30, fr / 16);
     auto al = [](uint64_t x) { return (x + 255) & ~255ull; };
     std::vector<Group> groups;
     {
@@ -651,10 +651,10 @@ static int batch_host(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg, const uint8_t *bas
         }
         if (g.count) groups.push_back(g);
     }
-    constexpr int NBUF = 3;
+    constexpr int NBUF = 6;   // staged groups in flight: their SHA tails overlap the next groups' copies
     uint64_t buf_bytes = 256;
     for (auto &g : groups) buf_bytes = std::max(buf_bytes, g.bytes);
-    uint8_t *bufs[NBUF] = {nullptr, nullptr, nullptr};
+    uint8_t *bufs[NBUF] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int nbuf = (int)std::min<size_t>(NBUF, groups.size());
     for (int b = 0; b < nbuf; b++) {
         bufs[b] = (uint8_t *)ctx->dev.get(buf_bytes);

@@ -46,7 +46,8 @@ cudaError_t launch_set_make_keys(const uint8_t *d32, uint64_t n, uint64_t *tag, 
 // phase 0: mark in-batch duplicates + probe representatives.  phase 1: insert missing representatives.
 template <int PHASE>
 __global__ void k_set_process(SetTable t, const uint8_t *d32, const uint64_t *tag_sorted, const uint32_t *idx_sorted,
-                              uint64_t n, uint8_t *hit, uint8_t *is_rep_miss, unsigned long long *n_new) {
+                              uint64_t n, int do_insert, uint8_t *hit, uint8_t *is_rep_miss,
+                              unsigned long long *n_new) {
     uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     const uint32_t i = idx_sorted[j];
@@ -54,8 +55,9 @@ __global__ void k_set_process(SetTable t, const uint8_t *d32, const uint64_t *ta
     const uint64_t tag = tag_sorted[j];
     if (PHASE == 0) {
         // representative = first (lowest index: the sort is stable) of its equal-digest run
+        // (pure probe: plain membership, every element looks itself up)
         bool dup = false;
-        if (j > 0 && tag_sorted[j - 1] == tag) {
+        if (do_insert && j > 0 && tag_sorted[j - 1] == tag) {
             // equal tags are adjacent; normally equal digests too.  Walk back over the tag run only while
             // digests differ (a 64-bit tag collision between distinct digests -- practically never).
             for (uint64_t k = j; k > 0 && tag_sorted[k - 1] == tag; k--) {
@@ -98,8 +100,8 @@ cudaError_t launch_set_mark_probe_insert(SetTable t, const uint8_t *d32, const u
                                          cudaStream_t st) {
     if (!n) return cudaSuccess;
     unsigned blocks = (unsigned)((n + 255) / 256);
-    k_set_process<0><<<blocks, 256, 0, st>>>(t, d32, tag_sorted, idx_sorted, n, hit, is_rep_miss, n_new);
-    if (do_insert) k_set_process<1><<<blocks, 256, 0, st>>>(t, d32, tag_sorted, idx_sorted, n, hit, is_rep_miss, n_new);
+    k_set_process<0><<<blocks, 256, 0, st>>>(t, d32, tag_sorted, idx_sorted, n, do_insert, hit, is_rep_miss, n_new);
+    if (do_insert) k_set_process<1><<<blocks, 256, 0, st>>>(t, d32, tag_sorted, idx_sorted, n, do_insert, hit, is_rep_miss, n_new);
     return cudaGetLastError();
 }
 
