@@ -1,0 +1,134 @@
+// pbsgpu.hpp -- C++ host mirror of the reference's Go surface for the hot path, over the C ABI.
+//
+// The reference is compiled Go and the build image has no Go toolchain, so the host side above
+// the C ABI is written in C++ (header only).  Names, argument meaning and error behaviour follow
+// the Go call sites in the reference (internal/pxarmount/commit.go):
+//     buzhash.NewConfig(4096)                                   :302-305
+//     transfer.NewRemoteDedupSplitArchiveWriter(..., origPayloadIdx)   :329
+//     writer.WriteEntryReader(entry, reader, size)               :720, :858
+//     writer.Finish()                                            :383
+// Go `error` returns become pbsgpu::Error exceptions carrying the same text a Go caller would wrap.
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <functional>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "pbsgpu.h"
+
+namespace pbsgpu {
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string &m) : std::runtime_error(m), code(c) {}
+};
+
+namespace buzhash {
+using Config = pbsgpu_cfg;
+// buzhash.NewConfig(avgKiB) (Config, error)
+inline Config NewConfig(int avg_kib) {
+    Config c;
+    int rc = pbsgpu_config_kib((uint32_t)avg_kib, nullptr, &c);
+    if (rc) throw Error(rc, "buzhash: invalid average chunk size " + std::to_string(avg_kib) + " KiB");
+    return c;
+}
+}  // namespace buzhash
+
+class Engine {
+  public:
+    explicit Engine(int device = 0) {
+        int rc = pbsgpu_open(device, &ctx_);
+        if (rc) throw Error(rc, "pbsgpu_open: no usable CUDA device (there is no CPU fallback)");
+    }
+    ~Engine() { pbsgpu_close(ctx_); }
+    Engine(const Engine &) = delete;
+    Engine &operator=(const Engine &) = delete;
+    pbsgpu_ctx *ctx() const { return ctx_; }
+    void check(int rc) const { if (rc) throw Error(rc, std::string("pbsgpu: ") + pbsgpu_strerror(ctx_)); }
+
+  private:
+    pbsgpu_ctx *ctx_ = nullptr;
+};
+
+class KnownSet {   // the session's known-chunk set (PreviousBackupRef, commit.go:286-294)
+  public:
+    explicit KnownSet(Engine &e, uint64_t hint = 1 << 16) : e_(e) { e.check(pbsgpu_set_create(e.ctx(), hint, &s_)); }
+    ~KnownSet() { pbsgpu_set_destroy(s_); }
+    pbsgpu_set *handle() const { return s_; }
+    uint64_t SeedFromDidx(const std::vector<uint8_t> &didx) {   // origPayloadIdx, commit.go:324-328
+        uint64_t n = 0;
+        if (!didx.empty()) e_.check(pbsgpu_set_seed_didx(s_, didx.data(), didx.size(), &n));
+        return n;
+    }
+    uint64_t size() const { uint64_t c = 0; pbsgpu_set_count(s_, &c); return c; }
+
+  private:
+    Engine &e_;
+    pbsgpu_set *s_ = nullptr;
+};
+
+namespace transfer {
+
+struct Entry { std::string Path; uint64_t FileSize; };   // the fields of pxar.Entry the hot path reads
+struct IndexRecord { std::string path; uint64_t end_off; uint8_t digest[32]; bool known; };
+// io.Reader: fill buf[0..n) and return the number of bytes produced (0 = EOF)
+using Reader = std::function<size_t(uint8_t *buf, size_t n)>;
+
+class DedupWriter {
+  public:
+    DedupWriter(Engine &e, const buzhash::Config &cfg, KnownSet *known, uint64_t staging_bytes = 1ull << 30)
+        : e_(e), cfg_(cfg), known_(known), cap_(staging_bytes) {
+        buf_ = (uint8_t *)pbsgpu_host_alloc(e.ctx(), cap_);
+        if (!buf_) throw Error(PBSGPU_ENOMEM, "pbsgpu: pinned staging allocation failed");
+    }
+    ~DedupWriter() { pbsgpu_host_free(e_.ctx(), buf_); }
+
+    // writer.WriteEntryReader(entry, reader, size): pulls exactly `size` bytes (io.ReadFull semantics)
+    void WriteEntryReader(const Entry &entry, const Reader &reader, uint64_t size) {
+        if (finished_) throw Error(PBSGPU_ESTATE, "transfer: writer already finished");
+        uint64_t start = (fill_ + 255) & ~255ull;
+        if (start + size > cap_) { Flush(); start = 0; }
+        if (size > cap_) throw Error(PBSGPU_ENOMEM, "transfer: entry larger than the staging buffer: " + entry.Path);
+        uint64_t got = 0;
+        while (got < size) {
+            size_t k = reader(buf_ + start + got, size - got);
+            if (k == 0) throw Error(PBSGPU_EINVAL, "transfer: short read for " + entry.Path + ": unexpected EOF");
+            got += k;
+        }
+        entries_.push_back(entry); off_.push_back(start); len_.push_back(size);
+        fill_ = start + size;
+    }
+    void Flush() {
+        if (entries_.empty()) return;
+        uint64_t cap = entries_.size();
+        for (uint64_t l : len_) cap += l / (cfg_.min > 64 ? cfg_.min : 65);
+        std::vector<pbsgpu_chunk> out(cap + 1);
+        uint64_t n = 0;
+        e_.check(pbsgpu_chunk_digest_batch(e_.ctx(), &cfg_, buf_, off_.data(), len_.data(), (uint32_t)entries_.size(),
+                                           known_ ? known_->handle() : nullptr, out.data(), out.size(), &n));
+        for (uint64_t i = 0; i < n; i++) {
+            IndexRecord r;
+            r.path = entries_[out[i].stream].Path; r.end_off = out[i].end_off;
+            std::memcpy(r.digest, out[i].digest, 32); r.known = (out[i].flags & PBSGPU_CHUNK_KNOWN) != 0;
+            index_.push_back(r);
+        }
+        entries_.clear(); off_.clear(); len_.clear(); fill_ = 0;
+    }
+    const std::vector<IndexRecord> &Finish() { Flush(); finished_ = true; return index_; }
+
+  private:
+    Engine &e_;
+    buzhash::Config cfg_;
+    KnownSet *known_;
+    uint8_t *buf_ = nullptr;
+    uint64_t cap_, fill_ = 0;
+    bool finished_ = false;
+    std::vector<Entry> entries_;
+    std::vector<uint64_t> off_, len_;
+    std::vector<IndexRecord> index_;
+};
+
+}  // namespace transfer
+}  // namespace pbsgpu

@@ -54,6 +54,21 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB
 
 
+def build_cxx_driver() -> Path:
+    """C++ caller of the C ABI through include/pbsgpu.hpp (stands in for the Go caller)."""
+    root = HERE.parent
+    src, out = root / "tests" / "cxx" / "driver.cpp", root / "tests" / "cxx" / "driver.bin"
+    if not src.exists():
+        return out
+    dep = max(src.stat().st_mtime, (root / "include" / "pbsgpu.hpp").stat().st_mtime,
+              (root / "include" / "pbsgpu.h").stat().st_mtime)
+    if not out.exists() or out.stat().st_mtime < dep:
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", str(out), str(src), f"-L{HERE}", "-lpbsgpu",
+                               "-Wl,-rpath,$ORIGIN/../../pbs_plus_b200"])
+    return out
+
+
 if __name__ == "__main__":
     p = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    build_cxx_driver()
     print(p)

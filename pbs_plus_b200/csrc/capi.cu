@@ -70,7 +70,7 @@ struct Pool {
     }
 };
 
-constexpr int N_STREAMS = 4;
+constexpr int N_STREAMS = 32;   // jobs in flight overlap only if they sit on different streams
 
 struct pbsgpu_ctx {
     int device = 0;

@@ -254,17 +254,178 @@ __global__ void __launch_bounds__(32) k_sha_tuned(ShaArgs a, Opq o) {
     sha_finish(s, p + (uint64_t)nblk * 64, c.len & 63, c.len, a.digests + (uint64_t)id * 32);
 }
 
+// ---------------------------------------------------------------------------
+// Split kernel (default): the per-chunk SHA-256 chain is serial, so the batch's makespan
+// is bounded below by the LONGEST chunk (16 MiB) run by ONE lane.  A lone warp is limited
+// by its own dependent-issue rate (ALU instructions occupy the 16-lane pipe 2 clk each and
+// ncu shows ~0.38 IPC, stall reason "wait"), so the fewer instructions sit on the serial
+// chain the faster the tail.  Each CTA = 2 warps over the same 32 chunks, on different SM
+// sub-partitions (own ALU/FMA pipes each):
+//   warp 0 (producer): LDG.128 loads + prefetch, realign/byte-swap, message schedule,
+//                      W[i]+K[i]  -> shared-memory ring (STS.128, conflict free)
+//   warp 1 (consumer): only the 64 rounds (10 ALU + 7 FMA instructions per round),
+//                      reads W+K with LDS.128
+// hand-off through mbarriers (full/empty per stage, 32 arrivals each).  Total work is the
+// same as the single-warp kernel; the serial chain per block shrinks from ~1900 to ~1100
+// instructions.
+// ---------------------------------------------------------------------------
+constexpr int SPLIT_STAGES = 3;
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n .reg .pred P1;\n LAB_WAIT:\n"
+        " mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        " @P1 bra DONE;\n bra LAB_WAIT;\n DONE:\n }" ::"r"(bar), "r"(parity) : "memory");
+}
+
+// consumer: 64 rounds with W+K supplied.  CMODE 0: IADD3 forms (fewest instructions),
+// CMODE 1: all additions on the FMA pipe (a*1+b with an opaque 1).
+template <int CMODE>
+__device__ __forceinline__ void sha_rounds(Sha256State &s, const uint4 (&kwv)[16], const Opq &o) {
+    typedef Ops<CMODE ? 1 : 0> P;
+    uint32_t a = s.h[0], b = s.h[1], c = s.h[2], d = s.h[3], e = s.h[4], f = s.h[5], g = s.h[6], h = s.h[7];
+#pragma unroll
+    for (int i = 0; i < 64; i++) {
+        const uint4 v = kwv[i >> 2];
+        const uint32_t kw = (i & 3) == 0 ? v.x : (i & 3) == 1 ? v.y : (i & 3) == 2 ? v.z : v.w;
+        uint32_t hk = P::add(h, kw, o);            // off the critical path (h is 3 rounds old)
+        uint32_t dhk = P::add(d, hk, o);
+        uint32_t S1 = rotr(e, 6) ^ rotr(e, 11) ^ rotr(e, 25);
+        uint32_t ch = (e & f) ^ (~e & g);
+        uint32_t S0 = rotr(a, 2) ^ rotr(a, 13) ^ rotr(a, 22);
+        uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
+        uint32_t en, an;
+        if (CMODE) {
+            uint32_t s1ch = P::add(S1, ch, o);
+            en = P::add(s1ch, dhk, o);
+            uint32_t x = P::add(P::add(S0, mj, o), hk, o);
+            an = P::add(s1ch, x, o);
+        } else {
+            en = S1 + ch + dhk;                   // IADD3
+            uint32_t x = S0 + mj + hk;            // IADD3
+            an = x + S1 + ch;                     // IADD3
+        }
+        h = g; g = f; f = e; e = en; d = c; c = b; b = a; a = an;
+    }
+    s.h[0] += a; s.h[1] += b; s.h[2] += c; s.h[3] += d; s.h[4] += e; s.h[5] += f; s.h[6] += g; s.h[7] += h;
+}
+
+template <int PMODE, int CMODE>
+__global__ void __launch_bounds__(64) k_sha_split(ShaArgs a, Opq o) {
+    __shared__ __align__(16) uint4 ring[SPLIT_STAGES][16][32];   // [stage][4 rounds][lane] = W+K
+    __shared__ __align__(8) uint64_t bars[2 * SPLIT_STAGES];
+    unsigned long long n = *a.n_chunks;
+    if (n > a.chunk_cap) n = a.chunk_cap;
+    if ((uint64_t)blockIdx.x * 32 >= n) return;                  // whole CTA idle
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint64_t t = (uint64_t)blockIdx.x * 32 + lane;
+    const bool active = t < n;
+    uint32_t id = 0;
+    ChunkRef c; c.stream = 0; c.len = 0; c.start = 0;
+    if (active) { id = a.order ? a.order[t] : (uint32_t)t; c = a.chunks[id]; }
+    const uint8_t *p = a.base + ((a.off && active) ? a.off[c.stream] : 0) + c.start;
+    const uint32_t nblk = c.len >> 6;
+    const uint32_t nblk_max = __reduce_max_sync(0xffffffffu, nblk);
+    uint32_t full[SPLIT_STAGES], empty[SPLIT_STAGES];
+#pragma unroll
+    for (int k = 0; k < SPLIT_STAGES; k++) { full[k] = smem_addr(&bars[k]); empty[k] = smem_addr(&bars[SPLIT_STAGES + k]); }
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < SPLIT_STAGES; k++) { mbar_init(full[k], 32); mbar_init(empty[k], 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+        // ------------------------------ producer ------------------------------
+        constexpr uint32_t K[64] = {K256_LIST};
+        typedef Ops<PMODE> P;
+        const uint32_t delta = (uint32_t)((uintptr_t)p & 15), dw = delta >> 2, sh = delta & 3;
+        const uint4 *q = (const uint4 *)(p - delta);
+        const uint32_t sel = (sh + 3) | ((sh + 2) << 4) | ((sh + 1) << 8) | (sh << 12);
+        const bool need5 = delta != 0, d1 = dw & 1, d2 = dw & 2;
+        uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0, v2 = v0, v3 = v0, v4 = v0;
+        if (nblk) {
+            v0 = ldg128(q); v1 = ldg128(q + 1); v2 = ldg128(q + 2); v3 = ldg128(q + 3);
+            if (need5) v4 = ldg128(q + 4);
+        }
+        uint32_t stage = 0, phase = 0;
+        for (uint32_t b = 0; b < nblk_max; b++) {
+            mbar_wait(empty[stage], phase ^ 1);
+            if (b < nblk) {
+                uint32_t x[20] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w,
+                                  v3.x, v3.y, v3.z, v3.w, v4.x, v4.y, v4.z, v4.w};
+                if (b + 1 < nblk) {
+                    const uint4 *qn = q + (uint64_t)(b + 1) * 4;
+                    v0 = need5 ? v4 : ldg128(qn);
+                    v1 = ldg128(qn + 1); v2 = ldg128(qn + 2); v3 = ldg128(qn + 3);
+                    if (need5) v4 = ldg128(qn + 4);
+                }
+                uint32_t y[18], w[16];
+#pragma unroll
+                for (int i = 0; i < 18; i++) y[i] = d2 ? x[i + 2] : x[i];
+#pragma unroll
+                for (int i = 0; i < 17; i++) y[i] = d1 ? y[i + 1] : y[i];
+#pragma unroll
+                for (int i = 0; i < 16; i++) w[i] = __byte_perm(y[i], y[i + 1], sel);
+                uint32_t kw[4];
+#pragma unroll
+                for (int i = 0; i < 64; i++) {
+                    if (i >= 16) {
+                        uint32_t w15 = w[(i + 1) & 15], w2 = w[(i + 14) & 15];
+                        uint32_t s0 = rotr(w15, 7) ^ rotr(w15, 18) ^ P::shr3(w15, o);
+                        uint32_t s1 = rotr(w2, 17) ^ rotr(w2, 19) ^ P::shr10(w2, o);
+                        w[i & 15] = P::add(P::add(w[i & 15], s0, o), P::add(w[(i + 9) & 15], s1, o), o);
+                    }
+                    kw[i & 3] = P::add(w[i & 15], K[i], o);
+                    if ((i & 3) == 3) ring[stage][i >> 2][lane] = make_uint4(kw[0], kw[1], kw[2], kw[3]);
+                }
+            }
+            mbar_arrive(full[stage]);
+            if (++stage == SPLIT_STAGES) { stage = 0; phase ^= 1; }
+        }
+    } else {
+        // ------------------------------ consumer ------------------------------
+        Sha256State s;
+        sha_init(s);
+        uint32_t stage = 0, phase = 0;
+        for (uint32_t b = 0; b < nblk_max; b++) {
+            mbar_wait(full[stage], phase);
+            if (b < nblk) {
+                uint4 kwv[16];
+#pragma unroll
+                for (int k = 0; k < 16; k++) kwv[k] = ring[stage][k][lane];
+                sha_rounds<CMODE>(s, kwv, o);
+            }
+            mbar_arrive(empty[stage]);
+            if (++stage == SPLIT_STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (active) sha_finish(s, p + (uint64_t)nblk * 64, c.len & 63, c.len, a.digests + (uint64_t)id * 32);
+    }
+}
+
 static int g_sha_mode = -1;
 cudaError_t launch_sha_tuned(const ShaArgs &a, int sm_count, cudaStream_t st) {
     (void)sm_count;
     if (a.chunk_cap == 0) return cudaSuccess;
     if (g_sha_mode < 0) {
         const char *e = getenv("PBSGPU_SHA_MODE");
-        g_sha_mode = e ? atoi(e) : 7;
+        g_sha_mode = e ? atoi(e) : 13;
     }
     Opq o{1u, 1u << 29, 1u << 22, 1u << 7};
     unsigned blocks = (unsigned)((a.chunk_cap + 31) / 32);
     switch (g_sha_mode) {
+        case 10: k_sha_split<0, 0><<<blocks, 64, 0, st>>>(a, o); break;   // split, compiler's own pipe choice
+        case 11: k_sha_split<3, 0><<<blocks, 64, 0, st>>>(a, o); break;   // producer balanced, consumer IADD3
+        case 12: k_sha_split<0, 1><<<blocks, 64, 0, st>>>(a, o); break;
+        case 13: k_sha_split<3, 1><<<blocks, 64, 0, st>>>(a, o); break;   // both balanced
         case 0: k_sha_tuned<0><<<blocks, 32, 0, st>>>(a, o); break;
         case 1: k_sha_tuned<1><<<blocks, 32, 0, st>>>(a, o); break;
         case 3: k_sha_tuned<3><<<blocks, 32, 0, st>>>(a, o); break;

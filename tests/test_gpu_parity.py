@@ -384,3 +384,27 @@ def test_dedup_writer_mirror_of_the_reference_surface(eng):
     for d, b in uploaded.items():
         assert hashlib.sha256(b).digest() == d
     assert len(uploaded) == len({r.digest for r in index})
+
+
+def test_cxx_host_mirror_driver(tmp_path):
+    """The C++ mirror of the Go surface (include/pbsgpu.hpp) driving the C ABI from a non-Python
+    process, with pinned staging filled by the caller -- what the cgo shim does."""
+    import subprocess
+    drv = Path(__file__).parent / "cxx" / "driver.bin"
+    if not drv.exists():
+        pytest.skip("driver not built (run __graft_entry__.build())")
+    datas = {"f0.bin": rnd(3_000_000, 61), "f1.bin": rnd(10, 62), "f2.bin": rnd(0, 63), "f3.bin": rnd(777_777, 64)}
+    paths = []
+    for k, v in datas.items():
+        (tmp_path / k).write_bytes(v.tobytes())
+        paths.append(str(tmp_path / k))
+    out = subprocess.run([str(drv), "16", *paths], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.strip().splitlines()
+    assert lines[-1] == "config-error -22"
+    ref = oracle.chunk_digest_streams(oracle.config(16 << 10), list(datas.values()))
+    rows = [l.split() for l in lines[:-1]]
+    for ps in (0, 1):
+        got = [(r[1], int(r[2]), r[3], int(r[4])) for r in rows if int(r[0]) == ps]
+        assert [(g[1], g[2]) for g in got] == [(int(r["end_off"]), bytes(r["digest"]).hex()) for r in ref]
+        assert all(g[3] == ps for g in got)          # first pass: all new; second pass: all known
