@@ -79,6 +79,7 @@ struct pbsgpu_ctx {
     std::string err;
     std::recursive_mutex mu;
     cudaStream_t streams[N_STREAMS];
+    cudaStream_t streams2[N_STREAMS];   // forked side stream per job stream (latency kernel of the hybrid SHA launch)
     cudaStream_t copy_stream;
     int next_stream = 0;
     Pool dev, pin;
@@ -151,7 +152,8 @@ extern "C" int pbsgpu_open(int device, pbsgpu_ctx **out) {
     }
     ctx->sm_count = ctx->prop.multiProcessorCount;
     for (int i = 0; i < N_STREAMS; i++)
-        if (cudaStreamCreateWithFlags(&ctx->streams[i], cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PBSGPU_ECUDA; }
+        if (cudaStreamCreateWithFlags(&ctx->streams[i], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&ctx->streams2[i], cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PBSGPU_ECUDA; }
     if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PBSGPU_ECUDA; }
     if (cudaMalloc(&ctx->d_table, 1024) != cudaSuccess || cudaMalloc(&ctx->d_rot, 65536) != cudaSuccess) {
         delete ctx; return PBSGPU_ENOMEM;
@@ -170,7 +172,7 @@ extern "C" void pbsgpu_close(pbsgpu_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    for (int i = 0; i < N_STREAMS; i++) cudaStreamDestroy(ctx->streams[i]);
+    for (int i = 0; i < N_STREAMS; i++) { cudaStreamDestroy(ctx->streams[i]); cudaStreamDestroy(ctx->streams2[i]); }
     cudaStreamDestroy(ctx->copy_stream);
     cudaFree(ctx->d_table); cudaFree(ctx->d_rot);
     if (ctx->epoch) cudaEventDestroy(ctx->epoch);
@@ -222,11 +224,11 @@ static int upload_table(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg, cudaStream_t st)
 // ---------------------------------------------------------------------------
 // Job: one batch of device-resident streams through K1..K3 on one CUDA stream.
 // ---------------------------------------------------------------------------
-enum { EV_START, EV_SCAN, EV_SORT, EV_RESOLVE, EV_SHA, EV_END, EV_COUNT };
+enum { EV_START, EV_SCAN, EV_SORT, EV_RESOLVE, EV_SHA, EV_END, EV_FORK, EV_JOIN, EV_COUNT };
 
 struct pbsgpu_job {
     pbsgpu_ctx *ctx = nullptr;
-    cudaStream_t st = nullptr;
+    cudaStream_t st = nullptr, st2 = nullptr;
     pbsgpu_cfg cfg;
     const uint8_t *base = nullptr;
     std::vector<uint64_t> off, len, tile_first;
@@ -339,11 +341,12 @@ static int job_create(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg, const void *base_d
     j->cand_cap = expected_cand_cap(*cfg, total);
     if (j->cand_cap >= (1ull << 31)) { delete j; return fail(ctx, PBSGPU_EINVAL, "batch too large (candidate buffer)"); }
     j->st = ctx->streams[ctx->next_stream];
+    j->st2 = ctx->streams2[ctx->next_stream];
     ctx->next_stream = (ctx->next_stream + 1) % N_STREAMS;
     int rc = job_alloc(j);
     if (rc) { job_release(j); return rc; }
     for (int i = 0; i < EV_COUNT; i++)
-        if (cudaEventCreateWithFlags(&j->ev[i], j->profiling ? cudaEventDefault : cudaEventDisableTiming) != cudaSuccess) {
+        if (cudaEventCreateWithFlags(&j->ev[i], (j->profiling && i < EV_FORK) ? cudaEventDefault : cudaEventDisableTiming) != cudaSuccess) {
             for (int k = 0; k < i; k++) cudaEventDestroy(j->ev[k]);
             job_release(j);
             return fail(ctx, PBSGPU_ECUDA, "cudaEventCreate failed");
@@ -396,8 +399,23 @@ static int job_enqueue(pbsgpu_job *j) {
         ShaArgs ha;
         ha.base = j->base; ha.off = j->d_off; ha.chunks = j->d_chunks; ha.order = j->d_vals2;
         ha.n_chunks = &j->d_counters[1]; ha.chunk_cap = j->chunk_cap; ha.digests = j->d_digests;
+        ha.n_head = nullptr; ha.part = 0;
         if (j->variant == 1) CK(launch_sha_simple(ha, st));
-        else CK(launch_sha_tuned(ha, ctx->sm_count, st));
+        else if (!sha_hybrid_enabled()) CK(launch_sha_tuned(ha, ctx->sm_count, st));
+        else {
+            // hybrid: chunks longer than 2.5 x avg (their serial chains bound the batch's makespan) run on
+            // the latency-optimised split kernel on a forked stream, concurrently with the rest
+            uint64_t thr64 = (uint64_t)j->cfg.avg * 5 / 2;
+            uint32_t thr = thr64 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)thr64;
+            CK(launch_split_point(j->d_keys2, &j->d_counters[1], j->chunk_cap, thr, &j->d_counters[2], st));
+            CK(cudaEventRecord(j->ev[EV_FORK], st));
+            CK(cudaStreamWaitEvent(j->st2, j->ev[EV_FORK], 0));
+            ha.n_head = &j->d_counters[2];
+            ha.part = 1; CK(launch_sha_split(ha, j->st2));
+            CK(cudaEventRecord(j->ev[EV_JOIN], j->st2));
+            ha.part = 2; CK(launch_sha_tuned(ha, ctx->sm_count, st));
+            CK(cudaStreamWaitEvent(st, j->ev[EV_JOIN], 0));
+        }
     }
     if (j->profiling) CK(cudaEventRecord(j->ev[EV_SHA], st));
     if (j->want_digests)
@@ -441,7 +459,9 @@ static int job_finish(pbsgpu_job *j) {
     pbsgpu_timing &t = ctx->last_timing;
     memset(&t, 0, sizeof t);
     t.bytes = j->total_bytes; t.chunks = j->h_counters[1]; t.candidates = j->h_counters[0]; t.reruns = j->reruns;
-    t.scan_launches = 1; t.sha_launches = j->want_digests ? 1 : 0; t.other_launches = 3 + (j->want_digests ? 2 : 0);
+    t.scan_launches = 1;
+    t.sha_launches = j->want_digests ? (j->variant == 0 && sha_hybrid_enabled() ? 2 : 1) : 0;
+    t.other_launches = 3 + (j->want_digests ? 2 + (j->variant == 0 && sha_hybrid_enabled() ? 1 : 0) : 0);
     if (j->profiling) {
         cudaEventElapsedTime(&t.scan_ms, j->ev[EV_START], j->ev[EV_SCAN]);
         cudaEventElapsedTime(&t.sort_ms, j->ev[EV_SCAN], j->ev[EV_SORT]);
@@ -814,7 +834,7 @@ extern "C" int pbsgpu_sha256_batch(pbsgpu_ctx *ctx, const void *base, const uint
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_n, &hn, 8, cudaMemcpyHostToDevice, st);
         ShaArgs ha;
         ha.base = dbase; ha.off = nullptr; ha.chunks = d_refs; ha.order = nullptr; ha.n_chunks = d_n; ha.chunk_cap = n;
-        ha.digests = d_dig;
+        ha.digests = d_dig; ha.n_head = nullptr; ha.part = 0;
         if (e == cudaSuccess) e = ctx->variant == 1 ? launch_sha_simple(ha, st) : launch_sha_tuned(ha, ctx->sm_count, st);
         if (e == cudaSuccess) e = cudaMemcpyAsync(digests, d_dig, (uint64_t)n * 32, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);

@@ -74,9 +74,17 @@ struct ShaArgs {
     const unsigned long long *n_chunks;  // device count
     uint64_t chunk_cap;                  // launch bound
     uint8_t *digests;                    // [chunk_cap][32], indexed by chunk id
+    // hybrid launch: the first *n_head entries of `order` (the longest chunks) go to the
+    // latency-optimised split kernel (part 1), the rest to the throughput kernel (part 2).
+    const unsigned long long *n_head;    // device; NULL with part 0
+    int part;                            // 0 = everything, 1 = head only, 2 = everything but the head
 };
 cudaError_t launch_sha_simple(const ShaArgs &a, cudaStream_t st);
-cudaError_t launch_sha_tuned(const ShaArgs &a, int sm_count, cudaStream_t st);
+cudaError_t launch_sha_tuned(const ShaArgs &a, int sm_count, cudaStream_t st);   // throughput kernel
+cudaError_t launch_sha_split(const ShaArgs &a, cudaStream_t st);                 // latency kernel
+cudaError_t launch_split_point(const uint32_t *len_sorted_desc, const unsigned long long *n_chunks, uint64_t cap,
+                               uint32_t threshold, unsigned long long *n_head, cudaStream_t st);
+int sha_hybrid_enabled();
 cudaError_t launch_len_keys(const ChunkRef *chunks, const unsigned long long *n_chunks, uint64_t cap,
                             uint32_t *keys, uint32_t *vals, cudaStream_t st);
 cudaError_t launch_pack_chunks(const ChunkRef *chunks, const uint8_t *digests, const uint8_t *hit,

@@ -114,14 +114,23 @@ __device__ __forceinline__ void load_block_be(const uint8_t *p, uint32_t (&w)[16
     for (int i = 0; i < 16; i++) w[i] = __byte_perm(x[i], x[i + 1], sel);
 }
 
+// position in `order` handled by logical thread t of a launch, honouring the hybrid split
+__device__ __forceinline__ bool sha_slot(const ShaArgs &a, uint64_t t, uint64_t &pos) {
+    unsigned long long n = *a.n_chunks;
+    if (n > a.chunk_cap) n = a.chunk_cap;
+    unsigned long long head = a.part ? *a.n_head : 0ull;
+    if (head > n) head = n;
+    if (a.part == 1) { pos = t; return t < head; }
+    pos = t + head;
+    return pos < n;
+}
+
 // ---------------------------------------------------------------------------
 // Cross-check / v0 kernel: one thread per chunk, chunks in `order` (longest first).
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(64) k_sha_simple(ShaArgs a) {
-    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long n = *a.n_chunks;
-    if (n > a.chunk_cap) n = a.chunk_cap;
-    if (t >= n) return;
+    uint64_t t;
+    if (!sha_slot(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, t)) return;
     uint32_t id = a.order ? a.order[t] : (uint32_t)t;
     ChunkRef c = a.chunks[id];
     const uint8_t *p = a.base + (a.off ? a.off[c.stream] : 0) + c.start;
@@ -213,10 +222,8 @@ __device__ __forceinline__ uint4 ldg128(const uint4 *p) { return __ldg(p); }
 
 template <int MODE>
 __global__ void __launch_bounds__(32) k_sha_tuned(ShaArgs a, Opq o) {
-    uint64_t t = (uint64_t)blockIdx.x * 32 + threadIdx.x;
-    unsigned long long n = *a.n_chunks;
-    if (n > a.chunk_cap) n = a.chunk_cap;
-    if (t >= n) return;
+    uint64_t t;
+    if (!sha_slot(a, (uint64_t)blockIdx.x * 32 + threadIdx.x, t)) return;
     const uint32_t id = a.order ? a.order[t] : (uint32_t)t;
     const ChunkRef c = a.chunks[id];
     const uint8_t *p = a.base + (a.off ? a.off[c.stream] : 0) + c.start;
@@ -321,12 +328,11 @@ template <int PMODE, int CMODE>
 __global__ void __launch_bounds__(64) k_sha_split(ShaArgs a, Opq o) {
     __shared__ __align__(16) uint4 ring[SPLIT_STAGES][16][32];   // [stage][4 rounds][lane] = W+K
     __shared__ __align__(8) uint64_t bars[2 * SPLIT_STAGES];
-    unsigned long long n = *a.n_chunks;
-    if (n > a.chunk_cap) n = a.chunk_cap;
-    if ((uint64_t)blockIdx.x * 32 >= n) return;                  // whole CTA idle
+    uint64_t t0;
+    if (!sha_slot(a, (uint64_t)blockIdx.x * 32, t0)) return;    // whole CTA idle (uniform)
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint64_t t = (uint64_t)blockIdx.x * 32 + lane;
-    const bool active = t < n;
+    uint64_t t;
+    const bool active = sha_slot(a, (uint64_t)blockIdx.x * 32 + lane, t);
     uint32_t id = 0;
     ChunkRef c; c.stream = 0; c.len = 0; c.start = 0;
     if (active) { id = a.order ? a.order[t] : (uint32_t)t; c = a.chunks[id]; }
@@ -411,26 +417,67 @@ __global__ void __launch_bounds__(64) k_sha_split(ShaArgs a, Opq o) {
     }
 }
 
-static int g_sha_mode = -1;
+static int g_sha_mode = -1, g_sha_hybrid = -1;
+static void sha_env() {
+    if (g_sha_mode < 0) {
+        const char *e = getenv("PBSGPU_SHA_MODE");
+        g_sha_mode = e ? atoi(e) : 2;
+        const char *h = getenv("PBSGPU_SHA_HYBRID");
+        g_sha_hybrid = h ? atoi(h) : 1;
+    }
+}
+int sha_hybrid_enabled() { sha_env(); return g_sha_hybrid && g_sha_mode < 10; }
+
+// throughput kernel (mode 0: the compiler's own pipe choice; 2: + schedule shifts on the FMA pipe;
+// 1/3/7: more aggressive offloads, measured slower -- issue-rate bound)
 cudaError_t launch_sha_tuned(const ShaArgs &a, int sm_count, cudaStream_t st) {
     (void)sm_count;
     if (a.chunk_cap == 0) return cudaSuccess;
-    if (g_sha_mode < 0) {
-        const char *e = getenv("PBSGPU_SHA_MODE");
-        g_sha_mode = e ? atoi(e) : 13;
-    }
+    sha_env();
+    if (g_sha_mode >= 10 && a.part == 0) return launch_sha_split(a, st);
     Opq o{1u, 1u << 29, 1u << 22, 1u << 7};
     unsigned blocks = (unsigned)((a.chunk_cap + 31) / 32);
     switch (g_sha_mode) {
-        case 10: k_sha_split<0, 0><<<blocks, 64, 0, st>>>(a, o); break;   // split, compiler's own pipe choice
-        case 11: k_sha_split<3, 0><<<blocks, 64, 0, st>>>(a, o); break;   // producer balanced, consumer IADD3
-        case 12: k_sha_split<0, 1><<<blocks, 64, 0, st>>>(a, o); break;
-        case 13: k_sha_split<3, 1><<<blocks, 64, 0, st>>>(a, o); break;   // both balanced
         case 0: k_sha_tuned<0><<<blocks, 32, 0, st>>>(a, o); break;
         case 1: k_sha_tuned<1><<<blocks, 32, 0, st>>>(a, o); break;
         case 3: k_sha_tuned<3><<<blocks, 32, 0, st>>>(a, o); break;
-        default: k_sha_tuned<7><<<blocks, 32, 0, st>>>(a, o); break;
+        case 7: k_sha_tuned<7><<<blocks, 32, 0, st>>>(a, o); break;
+        default: k_sha_tuned<2><<<blocks, 32, 0, st>>>(a, o); break;
     }
+    return cudaGetLastError();
+}
+
+// latency kernel (producer/consumer warps)
+cudaError_t launch_sha_split(const ShaArgs &a, cudaStream_t st) {
+    if (a.chunk_cap == 0) return cudaSuccess;
+    sha_env();
+    Opq o{1u, 1u << 29, 1u << 22, 1u << 7};
+    unsigned blocks = (unsigned)((a.chunk_cap + 31) / 32);
+    switch (g_sha_mode) {
+        case 10: k_sha_split<0, 0><<<blocks, 64, 0, st>>>(a, o); break;
+        case 12: k_sha_split<0, 1><<<blocks, 64, 0, st>>>(a, o); break;
+        case 13: k_sha_split<3, 1><<<blocks, 64, 0, st>>>(a, o); break;
+        default: k_sha_split<3, 0><<<blocks, 64, 0, st>>>(a, o); break;   // producer balanced, consumer IADD3
+    }
+    return cudaGetLastError();
+}
+
+// number of leading entries (lengths sorted descending) longer than `threshold`, rounded up to 32
+__global__ void k_split_point(const uint32_t *len_sorted_desc, const unsigned long long *n_chunks, uint64_t cap,
+                              uint32_t threshold, unsigned long long *n_head) {
+    unsigned long long n = *n_chunks;
+    if (n > cap) n = cap;
+    unsigned long long lo = 0, hi = n;     // first index with len <= threshold
+    while (lo < hi) {
+        unsigned long long mid = (lo + hi) >> 1;
+        if (len_sorted_desc[mid] > threshold) lo = mid + 1; else hi = mid;
+    }
+    unsigned long long h = (lo + 31) & ~31ull;
+    *n_head = h > n ? n : h;
+}
+cudaError_t launch_split_point(const uint32_t *len_sorted_desc, const unsigned long long *n_chunks, uint64_t cap,
+                               uint32_t threshold, unsigned long long *n_head, cudaStream_t st) {
+    k_split_point<<<1, 1, 0, st>>>(len_sorted_desc, n_chunks, cap, threshold, n_head);
     return cudaGetLastError();
 }
 
