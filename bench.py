@@ -286,7 +286,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "how": "algorithmic bytes (1 per input byte) of all K launches / union of the launches' CUDA-event "
                    "intervals on their launching streams (launches of consecutive steps overlap)",
             "scan_kernel": {"achieved": scan_gbs, "frac": scan_gbs / peak},
-            "isolated_step_ms": {k: t_iso[k] for k in ("scan_ms", "sort_ms", "resolve_ms", "sha_ms", "total_ms")},
+            "isolated_step_ms": {k: t_iso[k] for k in ("scan_ms", "sort_ms", "resolve_ms", "sha_ms", "sha_long_ms",
+                                                        "sha_bulk_ms", "total_ms")},
         },
     }
     if rank == 0:

@@ -82,6 +82,7 @@ typedef struct pbsgpu_timing {
     /* kernel intervals in ms since the context was opened (same CUDA clock for all jobs of
      * a ctx): lets a caller merge overlapping jobs into "time a kernel class was active" */
     float scan_t0, scan_t1, sha_t0, sha_t1;
+    float sha_long_ms, sha_bulk_ms; /* hybrid SHA launch: latency kernel (long chunks) / throughput kernel */
     uint64_t bytes, chunks, candidates;
     uint32_t scan_launches, sha_launches, other_launches, reruns;
 } pbsgpu_timing;

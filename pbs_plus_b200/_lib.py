@@ -45,7 +45,8 @@ class DevInfo(C.Structure):
 class Timing(C.Structure):
     _fields_ = [("scan_ms", C.c_float), ("sort_ms", C.c_float), ("resolve_ms", C.c_float), ("sha_ms", C.c_float),
                 ("set_ms", C.c_float), ("total_ms", C.c_float), ("scan_t0", C.c_float), ("scan_t1", C.c_float),
-                ("sha_t0", C.c_float), ("sha_t1", C.c_float), ("bytes", C.c_uint64), ("chunks", C.c_uint64),
+                ("sha_t0", C.c_float), ("sha_t1", C.c_float), ("sha_long_ms", C.c_float), ("sha_bulk_ms", C.c_float),
+                ("bytes", C.c_uint64), ("chunks", C.c_uint64),
                 ("candidates", C.c_uint64), ("scan_launches", C.c_uint32), ("sha_launches", C.c_uint32),
                 ("other_launches", C.c_uint32), ("reruns", C.c_uint32)]
 

@@ -151,9 +151,13 @@ extern "C" int pbsgpu_open(int device, pbsgpu_ctx **out) {
         (void)cudaGetLastError(); delete ctx; return PBSGPU_ENODEV;
     }
     ctx->sm_count = ctx->prop.multiProcessorCount;
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    const char *pe = getenv("PBSGPU_HYBRID_PRIO");
+    int side_prio = (pe && atoi(pe)) ? prio_hi : prio_lo;   // 1: long-chunk kernels get the high-priority stream
     for (int i = 0; i < N_STREAMS; i++)
         if (cudaStreamCreateWithFlags(&ctx->streams[i], cudaStreamNonBlocking) != cudaSuccess ||
-            cudaStreamCreateWithFlags(&ctx->streams2[i], cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PBSGPU_ECUDA; }
+            cudaStreamCreateWithPriority(&ctx->streams2[i], cudaStreamNonBlocking, side_prio) != cudaSuccess) { delete ctx; return PBSGPU_ECUDA; }
     if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PBSGPU_ECUDA; }
     if (cudaMalloc(&ctx->d_table, 1024) != cudaSuccess || cudaMalloc(&ctx->d_rot, 65536) != cudaSuccess) {
         delete ctx; return PBSGPU_ENOMEM;
@@ -224,7 +228,7 @@ static int upload_table(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg, cudaStream_t st)
 // ---------------------------------------------------------------------------
 // Job: one batch of device-resident streams through K1..K3 on one CUDA stream.
 // ---------------------------------------------------------------------------
-enum { EV_START, EV_SCAN, EV_SORT, EV_RESOLVE, EV_SHA, EV_END, EV_FORK, EV_JOIN, EV_COUNT };
+enum { EV_START, EV_SCAN, EV_SORT, EV_RESOLVE, EV_SHA, EV_END, EV_FORK, EV_JOIN, EV_BULK, EV_COUNT };
 
 struct pbsgpu_job {
     pbsgpu_ctx *ctx = nullptr;
@@ -346,7 +350,7 @@ static int job_create(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg, const void *base_d
     int rc = job_alloc(j);
     if (rc) { job_release(j); return rc; }
     for (int i = 0; i < EV_COUNT; i++)
-        if (cudaEventCreateWithFlags(&j->ev[i], (j->profiling && i < EV_FORK) ? cudaEventDefault : cudaEventDisableTiming) != cudaSuccess) {
+        if (cudaEventCreateWithFlags(&j->ev[i], j->profiling ? cudaEventDefault : cudaEventDisableTiming) != cudaSuccess) {
             for (int k = 0; k < i; k++) cudaEventDestroy(j->ev[k]);
             job_release(j);
             return fail(ctx, PBSGPU_ECUDA, "cudaEventCreate failed");
@@ -405,16 +409,21 @@ static int job_enqueue(pbsgpu_job *j) {
         else {
             // hybrid: chunks longer than 2.5 x avg (their serial chains bound the batch's makespan) run on
             // the latency-optimised split kernel on a forked stream, concurrently with the rest
-            uint64_t thr64 = (uint64_t)j->cfg.avg * 5 / 2;
+            static int thr_x10 = -1, serial = -1;
+            if (thr_x10 < 0) { const char *e = getenv("PBSGPU_HYBRID_THR_X10"); thr_x10 = e ? atoi(e) : 25;
+                               const char *s2 = getenv("PBSGPU_HYBRID_SERIAL"); serial = s2 ? atoi(s2) : 0; }
+            cudaStream_t side = serial ? st : j->st2;
+            uint64_t thr64 = (uint64_t)j->cfg.avg * (uint64_t)thr_x10 / 10;
             uint32_t thr = thr64 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)thr64;
             CK(launch_split_point(j->d_keys2, &j->d_counters[1], j->chunk_cap, thr, &j->d_counters[2], st));
             CK(cudaEventRecord(j->ev[EV_FORK], st));
-            CK(cudaStreamWaitEvent(j->st2, j->ev[EV_FORK], 0));
+            if (!serial) CK(cudaStreamWaitEvent(side, j->ev[EV_FORK], 0));
             ha.n_head = &j->d_counters[2];
-            ha.part = 1; CK(launch_sha_split(ha, j->st2));
-            CK(cudaEventRecord(j->ev[EV_JOIN], j->st2));
+            ha.part = 1; CK(launch_sha_split(ha, side));
+            CK(cudaEventRecord(j->ev[EV_JOIN], side));
             ha.part = 2; CK(launch_sha_tuned(ha, ctx->sm_count, st));
-            CK(cudaStreamWaitEvent(st, j->ev[EV_JOIN], 0));
+            CK(cudaEventRecord(j->ev[EV_BULK], st));
+            if (!serial) CK(cudaStreamWaitEvent(st, j->ev[EV_JOIN], 0));
         }
     }
     if (j->profiling) CK(cudaEventRecord(j->ev[EV_SHA], st));
@@ -472,6 +481,11 @@ static int job_finish(pbsgpu_job *j) {
         cudaEventElapsedTime(&t.scan_t1, ctx->epoch, j->ev[EV_SCAN]);
         cudaEventElapsedTime(&t.sha_t0, ctx->epoch, j->ev[EV_RESOLVE]);
         cudaEventElapsedTime(&t.sha_t1, ctx->epoch, j->ev[EV_SHA]);
+        if (j->want_digests && j->variant == 0 && sha_hybrid_enabled() && j->chunk_cap) {
+            cudaEventElapsedTime(&t.sha_long_ms, j->ev[EV_FORK], j->ev[EV_JOIN]);
+            cudaEventElapsedTime(&t.sha_bulk_ms, j->ev[EV_FORK], j->ev[EV_BULK]);
+            (void)cudaGetLastError();
+        }
     }
     return PBSGPU_OK;
 }

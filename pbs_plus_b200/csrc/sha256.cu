@@ -447,19 +447,37 @@ cudaError_t launch_sha_tuned(const ShaArgs &a, int sm_count, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-// latency kernel (producer/consumer warps)
+// latency kernel (producer/consumer warps).
+// When it is launched next to a kernel that already occupies every SM, the CTA scheduler packs its
+// few CTAs onto a handful of SMs (measured: 4x slower than on an empty GPU).  In the hybrid launch
+// (part 1) each CTA therefore also asks for more than half an SM's shared memory, which caps it at
+// ONE CTA per SM and forces the spread; the throughput kernel uses no shared memory and still
+// co-resides.
+constexpr int SPLIT_SPREAD_SMEM = 112 * 1024;
+template <int PM, int CM>
+static cudaError_t launch_split_t(const ShaArgs &a, const Opq &o, unsigned blocks, cudaStream_t st) {
+    size_t dyn = 0;
+    static int spread = -1;
+    if (spread < 0) { const char *e = getenv("PBSGPU_SPLIT_SPREAD"); spread = e ? atoi(e) : 1; }
+    if (a.part == 1 && spread) {
+        dyn = SPLIT_SPREAD_SMEM;
+        cudaError_t e = cudaFuncSetAttribute(k_sha_split<PM, CM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        if (e != cudaSuccess) return e;
+    }
+    k_sha_split<PM, CM><<<blocks, 64, dyn, st>>>(a, o);
+    return cudaGetLastError();
+}
 cudaError_t launch_sha_split(const ShaArgs &a, cudaStream_t st) {
     if (a.chunk_cap == 0) return cudaSuccess;
     sha_env();
     Opq o{1u, 1u << 29, 1u << 22, 1u << 7};
     unsigned blocks = (unsigned)((a.chunk_cap + 31) / 32);
     switch (g_sha_mode) {
-        case 10: k_sha_split<0, 0><<<blocks, 64, 0, st>>>(a, o); break;
-        case 12: k_sha_split<0, 1><<<blocks, 64, 0, st>>>(a, o); break;
-        case 13: k_sha_split<3, 1><<<blocks, 64, 0, st>>>(a, o); break;
-        default: k_sha_split<3, 0><<<blocks, 64, 0, st>>>(a, o); break;   // producer balanced, consumer IADD3
+        case 10: return launch_split_t<0, 0>(a, o, blocks, st);
+        case 12: return launch_split_t<0, 1>(a, o, blocks, st);
+        case 13: return launch_split_t<3, 1>(a, o, blocks, st);
+        default: return launch_split_t<3, 0>(a, o, blocks, st);   // producer balanced, consumer IADD3
     }
-    return cudaGetLastError();
 }
 
 // number of leading entries (lengths sorted descending) longer than `threshold`, rounded up to 32

@@ -61,7 +61,9 @@ def global_known_flags(digest_set, all_digests, counts, rank: int) -> np.ndarray
     """Insert the globally ordered digest list into this rank's replicated set (on the GPU) and
     return the KNOWN flags of this rank's own chunks."""
     if hasattr(all_digests, "is_cuda") and all_digests.is_cuda:
-        import ctypes as C
+        import torch
+        # the gather ran on torch's stream; the library's kernels run on its own streams
+        torch.cuda.current_stream(all_digests.device).synchronize()
         n = int(all_digests.shape[0])
         hit = np.zeros(n, dtype=np.uint8)
         eng = digest_set._eng

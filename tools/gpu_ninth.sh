@@ -1,0 +1,19 @@
+#!/bin/bash
+mkdir -p gpurun_out
+show() { python - "$1" "$2" <<'PY'
+import json,sys
+f,tag=sys.argv[1],sys.argv[2]
+try:
+    d = json.loads(open(f).read().strip().splitlines()[-1])
+    print(tag, "value", round(d["value"],1), "ms/step", round(d["ms_per_step"],1), "iso", {k: round(v,1) for k,v in d["roofline"]["isolated_step_ms"].items()}, "lat", round(d["single_batch_latency_ms"]))
+except Exception as e:
+    print(tag, "failed", e); print(open(f).read()[-1500:])
+PY
+}
+run() { tag=$1; steps=$2; shift; shift; env "$@" timeout 600 python bench.py --steps $steps --warmup 1 --no-e2e --no-cpu > gpurun_out/b9_$tag.txt 2>&1; show gpurun_out/b9_$tag.txt "$tag"; }
+run spread 4 PBSGPU_SHA_MODE=2
+run spread_thr20 4 PBSGPU_SHA_MODE=2 PBSGPU_HYBRID_THR_X10=20
+run spread_thr15 4 PBSGPU_SHA_MODE=2 PBSGPU_HYBRID_THR_X10=15
+run spread_K16 16 PBSGPU_SHA_MODE=2
+run spread_thr15_K16 16 PBSGPU_SHA_MODE=2 PBSGPU_HYBRID_THR_X10=15
+run nohyb_K16 16 PBSGPU_SHA_MODE=2 PBSGPU_SHA_HYBRID=0
