@@ -24,6 +24,10 @@ from pathlib import Path
 
 import numpy as np
 
+# 32 hardware work queues instead of the default 8: the engine keeps up to 28 CUDA streams busy and
+# streams that alias one queue serialise (must be set before the CUDA context exists)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
@@ -218,9 +222,13 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         launches["mine"] += 3    # K4: make_keys + mark/probe + insert
         return rec, t, flags
 
-    # ---- warm-up (untimed): W full steps, sequential
+    # ---- warm-up (untimed): W full steps, sequential, then one pipelined burst of K steps so that the
+    # library's scratch pool (device + pinned buffers, events) is populated for K jobs in flight
     for _ in range(args.warmup):
         finish(eng.submit(cfg, data, off, ln))
+    if not args.no_prewarm:
+        for j in [eng.submit(cfg, data, off, ln) for _ in range(min(args.steps, args.inflight))]:
+            finish(j)
     # latency of ONE isolated batch (includes the serial tail of the longest chunk)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -238,8 +246,14 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    jobs = [eng.submit(cfg, data, off, ln) for _ in range(args.steps)]
-    results = [finish(j) for j in jobs]
+    from collections import deque
+    q, results = deque(), []
+    for _ in range(args.steps):          # sliding window: at most `inflight` batches on the GPU at once
+        if len(q) >= args.inflight:
+            results.append(finish(q.popleft()))
+        q.append(eng.submit(cfg, data, off, ln))
+    while q:
+        results.append(finish(q.popleft()))
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -272,7 +286,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                         f"chunk (min avg/4, max 4*avg), chunk+SHA-256+probe, HBM-resident",
             "reduced_to_fit_hbm": reduced, "chunks_per_step": n_chunks, "parallelism": f"files sharded x{world}",
             "l2": "inputs (>= 64 GiB) far exceed the 126 MB L2; no flush needed",
-            "pipelining": "K steps submitted asynchronously, all complete inside the timed region",
+            "pipelining": "steps submitted asynchronously in a sliding window; all K complete inside the timed region",
+            "inflight": args.inflight, "sm_partition(long,bulk)": list(eng.partition_info()),
             "known_hit_rate_last_step": hit_last,
             "per_step_sha_interval_ms": [[round(t["sha_t0"], 1), round(t["sha_t1"], 1)] for t in timings],
         },
@@ -308,6 +323,59 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    eng.close()
+
+
+def run_cfg3(args):
+    """BASELINE config[2]: a 10 TB synthetic corpus with 30 % duplicate 4 MiB blocks (runs of 8), streamed
+    through HBM in 64 GiB batches generated on the device; reports throughput and the digest-set hit rate.
+    Not the default bench line (diagnostic / parity-at-scale run; see profiles/)."""
+    import torch
+
+    import pbs_plus_b200 as pg
+
+    torch.cuda.set_device(0)
+    eng = pg.Engine(0, profiling=False)
+    file_len, n_files = args.file_mib << 20, args.files
+    total = int(args.total_tb * 1e12)
+    n_batches = max(1, total // (n_files * file_len))
+    corp = pg.corpus(seed=3, file_len=file_len, block_len=4 << 20, run_blocks=8, dup_permille=300)
+    cfg = pg.buzhash.NewConfig(4096)
+    known = eng.digest_set(4 << 20)
+    bufs = [torch.empty(n_files * file_len, dtype=torch.uint8, device="cuda") for _ in range(2)]
+    off = np.arange(n_files, dtype=np.uint64) * file_len
+    ln = np.full(n_files, file_len, dtype=np.uint64)
+    jobs = [None, None]
+    chunks = hits = 0
+    gen_s = 0.0
+
+    def drain(slot):
+        nonlocal chunks, hits
+        if jobs[slot] is not None:
+            rec, _ = jobs[slot].wait()
+            flags = known.insert(rec["digest"])
+            chunks += len(rec); hits += int((flags != 0).sum())
+            jobs[slot] = None
+
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for b in range(n_batches):
+        slot = b & 1
+        drain(slot)
+        g0 = time.perf_counter()
+        eng.corpus_fill(corp, b * n_files, n_files, bufs[slot], file_len)
+        gen_s += time.perf_counter() - g0
+        jobs[slot] = eng.submit(cfg, bufs[slot], off, ln)
+    drain(0); drain(1)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    nbytes = n_batches * n_files * file_len
+    print(json.dumps({
+        "workload": f"cfg3: {nbytes / 1e12:.2f} TB corpus, 30% duplicate 4 MiB blocks in runs of 8, {n_batches} batches of "
+                    f"{n_files} x {args.file_mib} MiB, 1 GPU", "bytes": nbytes, "chunks": chunks,
+        "known_chunks": hits, "hit_rate": hits / max(1, chunks), "distinct_digests": len(known),
+        "wall_s": wall, "generation_s": gen_s, "GiB_per_s_incl_generation": nbytes / wall / GIB,
+        "GiB_per_s_excl_generation": nbytes / max(1e-9, wall - gen_s) / GIB}), flush=True)
     eng.close()
 
 
@@ -357,13 +425,20 @@ def main():
     ap.add_argument("--e2e-files", type=int, default=512)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--avg-kib", type=int, default=4096, help="diagnostic only; the metric is quoted at 4096")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3"])
+    ap.add_argument("--total-tb", type=float, default=10.0, help="cfg3 only")
+    ap.add_argument("--no-prewarm", action="store_true")
+    ap.add_argument("--inflight", type=int, default=12, help="batches in flight (<= 13 stream slots)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.impl == "reference":
+    if args.workload == "cfg3":
+        if rank == 0:
+            run_cfg3(args)
+    elif args.impl == "reference":
         run_reference(args, rank, world)
     else:
         run_ours(args, rank, local_rank, world)

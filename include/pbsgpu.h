@@ -94,6 +94,9 @@ void pbsgpu_close(pbsgpu_ctx *ctx);
 const char *pbsgpu_strerror(const pbsgpu_ctx *ctx);
 int pbsgpu_device_info(pbsgpu_ctx *ctx, pbsgpu_devinfo *out);
 int pbsgpu_set_profiling(pbsgpu_ctx *ctx, int on);
+/* SM partition in effect (CUDA green contexts; PBSGPU_PARTITION_SMS=n at open): SMs reserved for the
+ * long-chunk latency kernels / SMs for everything else; both 0 when the GPU is not partitioned. */
+int pbsgpu_partition_info(pbsgpu_ctx *ctx, int *long_sms, int *bulk_sms);
 /* 0 = tuned kernels (default), 1 = simple cross-check kernels (same results) */
 int pbsgpu_set_kernel_variant(pbsgpu_ctx *ctx, int variant);
 

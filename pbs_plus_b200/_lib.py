@@ -63,7 +63,7 @@ class Corpus(C.Structure):
 # every symbol include/pbsgpu.h declares (tests assert the .so exports all of them)
 SYMBOLS = [
     "pbsgpu_version", "pbsgpu_open", "pbsgpu_close", "pbsgpu_strerror", "pbsgpu_device_info",
-    "pbsgpu_set_profiling", "pbsgpu_set_kernel_variant", "pbsgpu_config", "pbsgpu_config_kib",
+    "pbsgpu_set_profiling", "pbsgpu_partition_info", "pbsgpu_set_kernel_variant", "pbsgpu_config", "pbsgpu_config_kib",
     "pbsgpu_default_table", "pbsgpu_chunk_digest_batch", "pbsgpu_batch_submit", "pbsgpu_batch_wait",
     "pbsgpu_scan_batch", "pbsgpu_sha256_batch", "pbsgpu_stream_open", "pbsgpu_stream_write",
     "pbsgpu_stream_poll", "pbsgpu_stream_finish", "pbsgpu_stream_close", "pbsgpu_set_create",
@@ -93,6 +93,7 @@ def lib() -> C.CDLL:
     L.pbsgpu_strerror.restype = C.c_char_p
     L.pbsgpu_device_info.argtypes = [vp, C.POINTER(DevInfo)]
     L.pbsgpu_set_profiling.argtypes = [vp, C.c_int]
+    L.pbsgpu_partition_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.pbsgpu_set_kernel_variant.argtypes = [vp, C.c_int]
     L.pbsgpu_config.argtypes = [C.c_uint32, u32p, C.POINTER(Cfg)]
     L.pbsgpu_config_kib.argtypes = [C.c_uint32, u32p, C.POINTER(Cfg)]

@@ -5,6 +5,7 @@
 // reference (internal/pxarmount/commit.go:296-329, :720).  Pure C++ over the CUDA
 // runtime; no torch types.  There is no CPU fallback anywhere in this file: every data
 // path launches the kernels in scan.cu / resolve.cu / sha256.cu / digestset.cu.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -70,7 +71,7 @@ struct Pool {
     }
 };
 
-constexpr int N_STREAMS = 32;   // jobs in flight overlap only if they sit on different streams
+constexpr int N_STREAMS = 13;   // main + side stream per slot: 28 streams (+ copy stream) <= 32 HW connections
 
 struct pbsgpu_ctx {
     int device = 0;
@@ -90,7 +91,12 @@ struct pbsgpu_ctx {
     uint32_t table_cache[256];
     bool table_valid = false;
     pbsgpu_timing last_timing;
+    struct pbsgpu_job *pending_back = nullptr;   // async job whose SHA half is not enqueued yet (see flush_pending)
     cudaEvent_t epoch = nullptr;   // recorded at open; kernel intervals are reported relative to it
+    // optional spatial partition (CUDA green contexts): `part_sms` SMs are reserved for the latency
+    // kernels of long chunks (streams2), everything else runs on the remaining SMs (streams)
+    int part_sms = 0, bulk_sms = 0;
+    CUgreenCtx g_long = nullptr, g_bulk = nullptr;
     uint64_t stage_bytes = 0;   // host-input staging size (0 = auto)
 };
 
@@ -137,9 +143,57 @@ static bool cfg_ok(const pbsgpu_cfg *c) {
            c->max == c->avg << 2 && c->mask == c->avg * 2u - 1u && c->break_min == c->mask - 2u && c->window == 64;
 }
 
+// Spatial partition with CUDA green contexts (driver API, resolved at run time so the library does
+// not link libcuda): long-chunk latency kernels get `want` SMs of their own, so they are neither
+// slowed by co-resident bulk warps nor packed onto a few SMs.  Returns false (and leaves the ctx
+// untouched) when the driver does not offer it.
+template <typename T> static T driver_ep(const char *name) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    return (T)p;
+}
+static bool make_partition(pbsgpu_ctx *ctx, int want) {
+    auto devget = driver_ep<CUresult (*)(CUdevice *, int)>("cuDeviceGet");
+    auto getRes = driver_ep<CUresult (*)(CUdevice, CUdevResource *, CUdevResourceType)>("cuDeviceGetDevResource");
+    auto split = driver_ep<CUresult (*)(CUdevResource *, unsigned *, const CUdevResource *, CUdevResource *, unsigned, unsigned)>("cuDevSmResourceSplitByCount");
+    auto genDesc = driver_ep<CUresult (*)(CUdevResourceDesc *, CUdevResource *, unsigned)>("cuDevResourceGenerateDesc");
+    auto gcreate = driver_ep<CUresult (*)(CUgreenCtx *, CUdevResourceDesc, CUdevice, unsigned)>("cuGreenCtxCreate");
+    auto gstream = driver_ep<CUresult (*)(CUstream *, CUgreenCtx, unsigned, int)>("cuGreenCtxStreamCreate");
+    if (!devget || !getRes || !split || !genDesc || !gcreate || !gstream) return false;
+    cudaFree(0);   // make sure the primary context exists
+    CUdevice dev;
+    CUdevResource all, grp[1], rest;
+    unsigned n = 1;
+    CUdevResourceDesc dA, dB;
+    if (devget(&dev, ctx->device) != CUDA_SUCCESS || getRes(dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return false;
+    if (split(grp, &n, &all, &rest, 0, (unsigned)want) != CUDA_SUCCESS || n < 1 || rest.sm.smCount == 0) return false;
+    if (genDesc(&dA, &grp[0], 1) != CUDA_SUCCESS || genDesc(&dB, &rest, 1) != CUDA_SUCCESS) return false;
+    if (gcreate(&ctx->g_long, dA, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return false;
+    if (gcreate(&ctx->g_bulk, dB, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return false;
+    for (int i = 0; i < N_STREAMS; i++) {
+        CUstream a, b;
+        if (gstream(&b, ctx->g_bulk, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) return false;
+        if (gstream(&a, ctx->g_long, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) return false;
+        ctx->streams[i] = (cudaStream_t)b;
+        ctx->streams2[i] = (cudaStream_t)a;
+    }
+    ctx->part_sms = (int)grp[0].sm.smCount;
+    ctx->bulk_sms = (int)rest.sm.smCount;
+    ctx->sm_count = ctx->bulk_sms;   // persistent kernels (scan) size their grid to the bulk partition
+    return true;
+}
+
 extern "C" int pbsgpu_open(int device, pbsgpu_ctx **out) {
     if (!out) return PBSGPU_EINVAL;
     *out = nullptr;
+    // Streams that share a hardware work queue serialise (false dependencies); the default is 8 queues.
+    // Only effective if the CUDA context has not been created yet -- hosts that initialise CUDA first
+    // (e.g. torch) should export CUDA_DEVICE_MAX_CONNECTIONS=32 themselves (bench.py does).
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { (void)cudaGetLastError(); return PBSGPU_ENODEV; }
     if (device < 0 || device >= n) return PBSGPU_ENODEV;
@@ -155,7 +209,11 @@ extern "C" int pbsgpu_open(int device, pbsgpu_ctx **out) {
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     const char *pe = getenv("PBSGPU_HYBRID_PRIO");
     int side_prio = (pe && atoi(pe)) ? prio_hi : prio_lo;   // 1: long-chunk kernels get the high-priority stream
-    for (int i = 0; i < N_STREAMS; i++)
+    // default: 24 SMs reserved for the long-chunk latency kernels (green contexts); 0 disables
+    const char *ps = getenv("PBSGPU_PARTITION_SMS");
+    int want_part = ps ? atoi(ps) : 24;
+    bool partitioned = want_part > 0 && want_part + 8 <= ctx->sm_count && make_partition(ctx, want_part);
+    for (int i = 0; i < N_STREAMS && !partitioned; i++)
         if (cudaStreamCreateWithFlags(&ctx->streams[i], cudaStreamNonBlocking) != cudaSuccess ||
             cudaStreamCreateWithPriority(&ctx->streams2[i], cudaStreamNonBlocking, side_prio) != cudaSuccess) { delete ctx; return PBSGPU_ECUDA; }
     if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PBSGPU_ECUDA; }
@@ -180,6 +238,10 @@ extern "C" void pbsgpu_close(pbsgpu_ctx *ctx) {
     cudaStreamDestroy(ctx->copy_stream);
     cudaFree(ctx->d_table); cudaFree(ctx->d_rot);
     if (ctx->epoch) cudaEventDestroy(ctx->epoch);
+    if (ctx->g_long || ctx->g_bulk) {
+        auto gdestroy = driver_ep<CUresult (*)(CUgreenCtx)>("cuGreenCtxDestroy");
+        if (gdestroy) { if (ctx->g_long) gdestroy(ctx->g_long); if (ctx->g_bulk) gdestroy(ctx->g_bulk); }
+    }
     ctx->dev.destroy(); ctx->pin.destroy();
     delete ctx;
 }
@@ -199,6 +261,12 @@ extern "C" int pbsgpu_device_info(pbsgpu_ctx *ctx, pbsgpu_devinfo *out) {
     CK(cudaMemGetInfo(&fr, &tot));
     out->free_mem = fr; out->total_mem = tot;
     strncpy(out->name, ctx->prop.name, sizeof out->name - 1);
+    return PBSGPU_OK;
+}
+extern "C" int pbsgpu_partition_info(pbsgpu_ctx *ctx, int *long_sms, int *bulk_sms) {
+    if (!ctx) return PBSGPU_EINVAL;
+    if (long_sms) *long_sms = ctx->part_sms;
+    if (bulk_sms) *bulk_sms = ctx->bulk_sms;
     return PBSGPU_OK;
 }
 extern "C" int pbsgpu_set_profiling(pbsgpu_ctx *ctx, int on) { if (!ctx) return PBSGPU_EINVAL; ctx->profiling = on != 0; return 0; }
@@ -228,7 +296,7 @@ static int upload_table(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg, cudaStream_t st)
 // ---------------------------------------------------------------------------
 // Job: one batch of device-resident streams through K1..K3 on one CUDA stream.
 // ---------------------------------------------------------------------------
-enum { EV_START, EV_SCAN, EV_SORT, EV_RESOLVE, EV_SHA, EV_END, EV_FORK, EV_JOIN, EV_BULK, EV_COUNT };
+enum { EV_START, EV_SCAN, EV_SORT, EV_RESOLVE, EV_SHA, EV_END, EV_FORK, EV_JOIN, EV_BULK, EV_BACK, EV_COUNT };
 
 struct pbsgpu_job {
     pbsgpu_ctx *ctx = nullptr;
@@ -254,13 +322,14 @@ struct pbsgpu_job {
     pbsgpu_chunk *h_out = nullptr;
     uint64_t *h_consumed = nullptr;
     cudaEvent_t ev[EV_COUNT];
-    bool have_events = false, profiling = false, enqueued = false;
+    bool have_events = false, profiling = false, enqueued = false, front_done = false, back_done = false;
     uint32_t reruns = 0;
 };
 
 static void job_release(pbsgpu_job *j) {
     if (!j) return;
     pbsgpu_ctx *c = j->ctx;
+    if (c->pending_back == j) c->pending_back = nullptr;
     void *devp[] = {j->d_off, j->d_len, j->d_tile_first, j->d_cand, j->d_cand_sorted, j->d_counters, j->d_counts,
                     j->d_chunk_first, j->d_consumed, j->d_chunks, j->d_keys, j->d_keys2, j->d_vals, j->d_vals2,
                     j->d_digests, j->d_out, j->d_temp};
@@ -360,7 +429,17 @@ static int job_create(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg, const void *base_d
     return PBSGPU_OK;
 }
 
-static int job_enqueue(pbsgpu_job *j) {
+// The hybrid SHA launch pays off when the long-chunk kernels have SMs of their own (partition); without
+// a partition their CTAs pin 137 KB of shared memory per SM for ~0.3 s and starve the whole-SM scan CTAs of
+// later batches (measured: 163 vs 143 ms/step).  PBSGPU_SHA_HYBRID=2 forces it on regardless.
+static bool hybrid_for(const pbsgpu_ctx *ctx) {
+    static int force = -1;
+    if (force < 0) { const char *e = getenv("PBSGPU_SHA_HYBRID"); force = (e && atoi(e) == 2) ? 1 : 0; }
+    return ctx->part_sms > 0 || force;
+}
+
+// front half: inputs -> K1 scan -> sort -> K2 resolve (chunk list known on the device afterwards)
+static int job_enqueue_front(pbsgpu_job *j) {
     pbsgpu_ctx *ctx = j->ctx;
     cudaStream_t st = j->st;
     const uint32_t n = j->n;
@@ -381,7 +460,7 @@ static int job_enqueue(pbsgpu_job *j) {
     sa.cand = j->d_cand; sa.cand_cap = j->cand_cap; sa.cand_count = &j->d_counters[0];
     if (j->variant == 1) CK(launch_scan_simple(sa, st));
     else CK(launch_scan_tuned(sa, ctx->d_rot, ctx->sm_count, st));
-    if (j->profiling) CK(cudaEventRecord(j->ev[EV_SCAN], st));
+    CK(cudaEventRecord(j->ev[EV_SCAN], st));   // also the "scan done" signal a predecessor's back half waits for
     // candidates -> sorted by (stream, position)
     size_t tb = j->temp_bytes;
     CK(cub::DeviceRadixSort::SortKeys(j->d_temp, tb, j->d_cand, j->d_cand_sorted, (int)j->cand_cap, 0, 64, st));
@@ -394,7 +473,18 @@ static int job_enqueue(pbsgpu_job *j) {
     ra.n_chunks = &j->d_counters[1];
     CK(launch_resolve(ra, st));
     if (j->profiling) CK(cudaEventRecord(j->ev[EV_RESOLVE], st));
-    // K3
+    j->front_done = true;
+    j->back_done = false;
+    return PBSGPU_OK;
+}
+
+// back half: K3 SHA-256 (hybrid launch) -> pack -> D2H of the results
+static int job_enqueue_back(pbsgpu_job *j) {
+    pbsgpu_ctx *ctx = j->ctx;
+    cudaStream_t st = j->st;
+    const uint32_t n = j->n;
+    size_t tb = j->temp_bytes;
+    if (j->profiling) CK(cudaEventRecord(j->ev[EV_BACK], st));
     if (j->want_digests && j->chunk_cap) {
         CK(launch_len_keys(j->d_chunks, &j->d_counters[1], j->chunk_cap, j->d_keys, j->d_vals, st));
         tb = j->temp_bytes;
@@ -405,7 +495,7 @@ static int job_enqueue(pbsgpu_job *j) {
         ha.n_chunks = &j->d_counters[1]; ha.chunk_cap = j->chunk_cap; ha.digests = j->d_digests;
         ha.n_head = nullptr; ha.part = 0;
         if (j->variant == 1) CK(launch_sha_simple(ha, st));
-        else if (!sha_hybrid_enabled()) CK(launch_sha_tuned(ha, ctx->sm_count, st));
+        else if (!sha_hybrid_enabled() || !hybrid_for(ctx)) CK(launch_sha_tuned(ha, ctx->sm_count, st));
         else {
             // hybrid: chunks longer than 2.5 x avg (their serial chains bound the batch's makespan) run on
             // the latency-optimised split kernel on a forked stream, concurrently with the rest
@@ -435,7 +525,27 @@ static int job_enqueue(pbsgpu_job *j) {
     if (!j->eof && n) CK(cudaMemcpyAsync(j->h_consumed, j->d_consumed, n * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(j->ev[EV_END], st));
     j->enqueued = true;
+    j->back_done = true;
     return PBSGPU_OK;
+}
+
+// Scans are whole-SM CTAs (207 KB shared memory, 49k registers) and cannot be placed on an SM that
+// SHA CTAs of earlier batches already fill, so a scan submitted behind running SHA work stalls the
+// pipeline.  The asynchronous API therefore keeps the back half (SHA) of the most recent job
+// pending until the NEXT job's scan has been enqueued (and makes it wait for that scan), so scans
+// always run ahead of the SHA work that would block them.
+static int flush_pending(pbsgpu_ctx *ctx, pbsgpu_job *successor) {
+    pbsgpu_job *p = ctx->pending_back;
+    if (!p) return PBSGPU_OK;
+    ctx->pending_back = nullptr;
+    if (successor) CK(cudaStreamWaitEvent(p->st, successor->ev[EV_SCAN], 0));
+    return job_enqueue_back(p);
+}
+
+static int job_enqueue(pbsgpu_job *j) {
+    int rc = job_enqueue_front(j);
+    if (rc) return rc;
+    return job_enqueue_back(j);
 }
 
 // Blocks until the job is done; reruns it with a larger candidate buffer if the
@@ -469,19 +579,20 @@ static int job_finish(pbsgpu_job *j) {
     memset(&t, 0, sizeof t);
     t.bytes = j->total_bytes; t.chunks = j->h_counters[1]; t.candidates = j->h_counters[0]; t.reruns = j->reruns;
     t.scan_launches = 1;
-    t.sha_launches = j->want_digests ? (j->variant == 0 && sha_hybrid_enabled() ? 2 : 1) : 0;
-    t.other_launches = 3 + (j->want_digests ? 2 + (j->variant == 0 && sha_hybrid_enabled() ? 1 : 0) : 0);
+    const bool hyb = j->variant == 0 && sha_hybrid_enabled() && hybrid_for(ctx);
+    t.sha_launches = j->want_digests ? (hyb ? 2 : 1) : 0;
+    t.other_launches = 3 + (j->want_digests ? 2 + (hyb ? 1 : 0) : 0);
     if (j->profiling) {
         cudaEventElapsedTime(&t.scan_ms, j->ev[EV_START], j->ev[EV_SCAN]);
         cudaEventElapsedTime(&t.sort_ms, j->ev[EV_SCAN], j->ev[EV_SORT]);
         cudaEventElapsedTime(&t.resolve_ms, j->ev[EV_SORT], j->ev[EV_RESOLVE]);
-        cudaEventElapsedTime(&t.sha_ms, j->ev[EV_RESOLVE], j->ev[EV_SHA]);
+        cudaEventElapsedTime(&t.sha_ms, j->ev[EV_BACK], j->ev[EV_SHA]);
         cudaEventElapsedTime(&t.total_ms, j->ev[EV_START], j->ev[EV_END]);
         cudaEventElapsedTime(&t.scan_t0, ctx->epoch, j->ev[EV_START]);
         cudaEventElapsedTime(&t.scan_t1, ctx->epoch, j->ev[EV_SCAN]);
-        cudaEventElapsedTime(&t.sha_t0, ctx->epoch, j->ev[EV_RESOLVE]);
+        cudaEventElapsedTime(&t.sha_t0, ctx->epoch, j->ev[EV_BACK]);
         cudaEventElapsedTime(&t.sha_t1, ctx->epoch, j->ev[EV_SHA]);
-        if (j->want_digests && j->variant == 0 && sha_hybrid_enabled() && j->chunk_cap) {
+        if (j->want_digests && hyb && j->chunk_cap) {
             cudaEventElapsedTime(&t.sha_long_ms, j->ev[EV_FORK], j->ev[EV_JOIN]);
             cudaEventElapsedTime(&t.sha_bulk_ms, j->ev[EV_FORK], j->ev[EV_BULK]);
             (void)cudaGetLastError();
@@ -505,8 +616,13 @@ extern "C" int pbsgpu_batch_submit(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg, const
     pbsgpu_job *j = nullptr;
     int rc = job_create(ctx, cfg, base_dev, off, len, n, 1, 1, &j);
     if (rc) return rc;
-    rc = job_enqueue(j);
+    rc = job_enqueue_front(j);
+    if (rc == PBSGPU_OK) rc = flush_pending(ctx, j);     // predecessor's SHA goes in behind this job's scan
     if (rc) { cudaStreamSynchronize(j->st); job_release(j); return rc; }
+    static int defer = -1;
+    if (defer < 0) { const char *e = getenv("PBSGPU_DEFER_SHA"); defer = e ? atoi(e) : 0; }   // measured: no gain
+    if (defer) ctx->pending_back = j;
+    else { rc = job_enqueue_back(j); if (rc) { cudaStreamSynchronize(j->st); job_release(j); return rc; } }
     *job = j;
     return PBSGPU_OK;
 }
@@ -515,7 +631,9 @@ extern "C" int pbsgpu_batch_wait(pbsgpu_job *j, pbsgpu_chunk *out, uint64_t cap,
     if (!j) return PBSGPU_EINVAL;
     pbsgpu_ctx *ctx = j->ctx;
     Guard g(ctx);
-    int rc = job_finish(j);
+    int rc = PBSGPU_OK;
+    if (ctx->pending_back == j) rc = flush_pending(ctx, nullptr);
+    if (rc == PBSGPU_OK) rc = job_finish(j);
     if (rc == PBSGPU_OK) {
         uint64_t nch = j->h_counters[1];
         if (n_out) *n_out = nch;

@@ -457,10 +457,10 @@ constexpr int SPLIT_SPREAD_SMEM = 112 * 1024;
 template <int PM, int CM>
 static cudaError_t launch_split_t(const ShaArgs &a, const Opq &o, unsigned blocks, cudaStream_t st) {
     size_t dyn = 0;
-    static int spread = -1;
-    if (spread < 0) { const char *e = getenv("PBSGPU_SPLIT_SPREAD"); spread = e ? atoi(e) : 1; }
+    static int spread = -1;   // KiB of dummy dynamic shared memory per CTA (0 = off); 112 -> 1 CTA/SM, 85 -> 2
+    if (spread < 0) { const char *e = getenv("PBSGPU_SPLIT_SPREAD_KB"); spread = e ? atoi(e) : 30; }   // 30 KiB -> 4 CTAs/SM
     if (a.part == 1 && spread) {
-        dyn = SPLIT_SPREAD_SMEM;
+        dyn = (size_t)spread * 1024;
         cudaError_t e = cudaFuncSetAttribute(k_sha_split<PM, CM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
         if (e != cudaSuccess) return e;
     }

@@ -90,6 +90,12 @@ class Engine:
         return {"device": d.device, "sm_count": d.sm_count, "cc": (d.cc_major, d.cc_minor),
                 "total_mem": d.total_mem, "free_mem": d.free_mem, "name": d.name.decode()}
 
+    def partition_info(self) -> tuple[int, int]:
+        """(SMs reserved for long-chunk kernels, SMs for the rest); (0, 0) if not partitioned."""
+        a, b = C.c_int(), C.c_int()
+        self._ck(self._L.pbsgpu_partition_info(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def set_profiling(self, on: bool):
         self._ck(self._L.pbsgpu_set_profiling(self._h, 1 if on else 0))
 
