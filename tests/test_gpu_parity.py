@@ -408,3 +408,31 @@ def test_cxx_host_mirror_driver(tmp_path):
         got = [(r[1], int(r[2]), r[3], int(r[4])) for r in rows if int(r[0]) == ps]
         assert [(g[1], g[2]) for g in got] == [(int(r["end_off"]), bytes(r["digest"]).hex()) for r in ref]
         assert all(g[3] == ps for g in got)          # first pass: all new; second pass: all known
+
+
+def test_empty_batch_and_many_tiny_streams(eng, torch):
+    cfg = pg.make_config(256)
+    assert len(eng.chunk_digest_batch(cfg, torch.zeros(16, dtype=torch.uint8, device="cuda"), [], [])) == 0
+    rng = np.random.default_rng(71)
+    arrs = [rnd(int(n), 1000 + i) for i, n in enumerate(rng.integers(0, 700, size=3000))]
+    buf, off, ln = pack(arrs, align=16)
+    rec = eng.chunk_digest_batch(cfg, to_dev(torch, buf), off, ln)
+    ref = oracle.chunk_digest_streams(oracle.config(256), arrs, threads=4)
+    assert rec.tobytes() == ref.tobytes()
+
+
+def test_partition_info_is_consistent(eng):
+    long_sms, bulk_sms = eng.partition_info()
+    total = eng.device_info()["sm_count"]
+    assert (long_sms, bulk_sms) == (0, 0) or (long_sms >= 8 and long_sms + bulk_sms <= 148 and bulk_sms == total)
+
+
+def test_all_long_chunks_take_the_latency_kernel(eng, torch):
+    """Constant data => every chunk is a forced cut at max (> 2.5 x avg): the whole batch goes through the
+    long-chunk (split) kernel when the hybrid launch is active; digests must still match."""
+    data = np.zeros(3_000_000, dtype=np.uint8)
+    data[::4099] = 7
+    for avg in (4096, 65536):
+        rec = eng.chunk_digest_batch(pg.make_config(avg), to_dev(torch, data), [0, 1_000_001], [1_000_001, 1_999_999])
+        ref = oracle.chunk_digest_streams(oracle.config(avg), [data[:1_000_001], data[1_000_001:]])
+        assert rec.tobytes() == ref.tobytes()
