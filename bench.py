@@ -275,6 +275,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     sha_union = union_ms([(t["sha_t0"], t["sha_t1"]) for t in timings])
     scan_union = union_ms([(t["scan_t0"], t["scan_t1"]) for t in timings])
     peak, peak_src = measured_peaks()
+    traffic, traffic_src = ncu_traffic() if (n_files == 1024 and args.file_mib == 64) else (None, None)
     sha_gbs = step_bytes * args.steps / (sha_union / 1e3) / 1e9 if sha_union > 0 else 0.0
     scan_gbs = step_bytes * args.steps / (scan_union / 1e3) / 1e9 if scan_union > 0 else 0.0
 
@@ -298,7 +299,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         "single_batch_latency_ms": iso_ms,
         "roofline": {
             "bound": "hbm", "kernel": "k_sha256 (dominant; instruction-bound integer work, see DESIGN.md)",
-            "achieved": sha_gbs, "peak": peak, "unit": "GB/s", "frac": sha_gbs / peak, "traffic": None,
+            "achieved": sha_gbs, "peak": peak, "unit": "GB/s", "frac": sha_gbs / peak, "traffic": traffic,
+            "traffic_source": traffic_src, "algorithmic_bytes_per_launch": step_bytes,
             "peak_source": peak_src,
             "how": "algorithmic bytes (1 per input byte) of all K launches / union of the launches' CUDA-event "
                    "intervals on their launching streams (launches of consecutive steps overlap)",
@@ -382,11 +384,17 @@ def run_cfg3(args):
 
 
 def run_e2e(args, eng, cfg, pg, torch):
-    """Same metric through the public C-ABI call with HOST buffers: every step copies that step's
-    inputs from pinned host memory to the device (inside pbsgpu_chunk_digest_batch, overlapped with
-    the kernels) and reads the chunk records back."""
+    """Same metric through the public C-ABI call with HOST buffers: every step is one blocking
+    pbsgpu_chunk_digest_batch call that copies that step's inputs from pinned host memory to the device
+    (staged in 4 GiB groups, overlapped with the kernels) and returns the chunk records to the host.
+    Two host threads with one context each issue the calls (the way a multi-worker Go caller would):
+    while one call drains the serial SHA tail of its last group, the other call's copies use the link."""
+    import threading
+
     file_len = args.file_mib << 20
     n = args.e2e_files
+    workers = max(1, args.e2e_threads)
+    engines = [eng] + [pg.Engine(eng.device) for _ in range(workers - 1)]
     try:
         host = eng.host_alloc(n * file_len)
     except Exception as e:   # not enough pinned memory on this host
@@ -396,24 +404,64 @@ def run_e2e(args, eng, cfg, pg, torch):
     eng.corpus_fill(pg.corpus(seed=2, file_len=file_len), 0, n, tmp, file_len)
     torch.from_numpy(np.asarray(host)).copy_(tmp)
     del tmp
+    torch.cuda.empty_cache()
     off = np.arange(n, dtype=np.uint64) * file_len
     ln = np.full(n, file_len, dtype=np.uint64)
-    known = eng.digest_set(1 << 16)
-    eng.chunk_digest_batch(cfg, host, off, ln, known)      # warm-up
+    sets = [e.digest_set(1 << 16) for e in engines]
+    for e, s in zip(engines, sets):
+        e.chunk_digest_batch(cfg, host, off, ln, s)      # warm-up (also populates each context's pools)
     torch.cuda.synchronize()
-    steps = max(1, args.e2e_steps)
+    steps = max(workers, args.e2e_steps)
+    nrec = [0] * workers
+    errs = []
+
+    def work(w):
+        try:
+            for _ in range(w, steps, workers):
+                nrec[w] = len(engines[w].chunk_digest_batch(cfg, host, off, ln, sets[w]))
+        except Exception as ex:   # pragma: no cover
+            errs.append(repr(ex))
+
     t0 = time.perf_counter()
-    nrec = 0
-    for _ in range(steps):
-        rec = eng.chunk_digest_batch(cfg, host, off, ln, known)
-        nrec = len(rec)
+    ths = [threading.Thread(target=work, args=(w,)) for w in range(workers)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    for s in sets:
+        s.close()
     eng.host_free(host)
+    for e in engines[1:]:
+        e.close()
+    if errs:
+        return {"value": None, "unit": "GiB/s", "error": errs[0]}
     return {"value": n * file_len * steps / dt / GIB, "unit": "GiB/s", "h2d_bytes_per_step": int(n * file_len),
-            "d2h_bytes_per_step": int(nrec * 48), "steps": steps,
-            "workload": f"{n} x {args.file_mib} MiB files of the cfg2 corpus per step from pinned host memory "
-                        f"(PCIe-bound)", "timer": "host wall clock around the blocking C-ABI calls"}
+            "d2h_bytes_per_step": int(nrec[0] * 48), "steps": steps, "host_threads": workers,
+            "workload": f"{n} x {args.file_mib} MiB files of the cfg2 corpus per step (one blocking C-ABI call) from "
+                        f"pinned host memory; PCIe-bound", "timer": "host wall clock around the blocking C-ABI calls"}
+
+
+def ncu_traffic():
+    """dram bytes (read+write) per launch of the SHA kernels from the committed ncu --set full summaries."""
+    import re
+    tot, used = 0.0, []
+    for name in ("r01_ncu_k_sha_tuned.txt", "r01_ncu_k_sha_split.txt"):
+        p = ROOT / "profiles" / name
+        if not p.exists():
+            return None, None
+        txt = p.read_text()
+        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            m = re.search(key + r"\s+(\w+)\s+([0-9.]+)", txt)
+            if not m:
+                return None, None
+            scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(m.group(1), None)
+            if scale is None:
+                return None, None
+            tot += float(m.group(2)) * scale
+        used.append(name)
+    return tot, "profiles/" + " + ".join(used) + " (one 64 GiB batch; both SHA kernels of the hybrid launch)"
 
 
 def main():
@@ -425,7 +473,8 @@ def main():
     ap.add_argument("--files", type=int, default=1024)
     ap.add_argument("--file-mib", type=int, default=64)
     ap.add_argument("--e2e-files", type=int, default=512)
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--e2e-threads", type=int, default=2)
     ap.add_argument("--avg-kib", type=int, default=4096, help="diagnostic only; the metric is quoted at 4096")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3"])
     ap.add_argument("--total-tb", type=float, default=10.0, help="cfg3 only")
