@@ -116,7 +116,6 @@ static int fail(pbsgpu_ctx *c, int code, const char *fmt, ...) {
             return fail(ctx, PBSGPU_ECUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
         }                                                                                              \
     } while (0)
-#define CKDEV(ctx) CK(cudaSetDevice((ctx)->device))
 
 struct Guard {   // one call at a time per ctx + device binding for this OS thread (goroutines migrate)
     std::lock_guard<std::recursive_mutex> lk;

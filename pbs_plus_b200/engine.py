@@ -170,9 +170,6 @@ class Engine:
                                              out.ctypes.data))
         return out
 
-    def last_timing(self) -> dict:
-        raise NotImplementedError("timing is returned by Job.wait()")
-
     # -- misc ---------------------------------------------------------------------------
     def digest_set(self, capacity_hint: int = 1 << 16) -> "DigestSet":
         return DigestSet(self, capacity_hint)
