@@ -171,6 +171,21 @@ int pbsgpu_set_count(pbsgpu_set *set, uint64_t *count);
  * {u64 end_le, digest[32]} entries (what origPayloadIdx holds, commit.go:324-329). */
 int pbsgpu_set_seed_didx(pbsgpu_set *set, const uint8_t *didx, uint64_t size, uint64_t *n_entries);
 
+/* ---- f1 ("next" row of SURVEY.md section 8): PBS dynamic index (.didx) images ----------------
+ * The (end offset, digest) list of a finished archive lands in `<name>.mpxar.didx` /
+ * `<name>.ppxar.didx` (names at commit.go:321-322; parsed via datastore.ParseDynamicIndex,
+ * internal/pxar/format.go:163).  Layout restated from upstream PBS (UNVERIFIED against the Go
+ * module): 4096-byte header { magic[8] = 1c 91 4e a5 19 ba b3 cd, uuid[16], ctime i64 LE,
+ * index_csum[32] = SHA-256 over the entry table, zero padding } followed by n entries
+ * { u64 end_le, digest[32] }.  Offsets are cumulative over the records in the order given (the
+ * archive stream is the concatenation of the streams).  The checksum is computed on the GPU. */
+uint64_t pbsgpu_didx_size(uint64_t n_entries);
+int pbsgpu_didx_build(pbsgpu_ctx *ctx, const pbsgpu_chunk *chunks, uint64_t n, const uint8_t uuid[16], int64_t ctime,
+                      uint8_t *out, uint64_t cap);
+/* ends / digests may be NULL to only count; verify != 0 recomputes index_csum (PBSGPU_EINVAL on mismatch). */
+int pbsgpu_didx_parse(pbsgpu_ctx *ctx, const uint8_t *didx, uint64_t size, uint64_t *ends, uint8_t *digests,
+                      uint64_t cap, uint64_t *n_entries, int verify);
+
 /* ---- pinned staging owned by C, filled by the Go side ----------------------------- */
 void *pbsgpu_host_alloc(pbsgpu_ctx *ctx, uint64_t bytes);
 void pbsgpu_host_free(pbsgpu_ctx *ctx, void *p);

@@ -91,3 +91,23 @@ def splitmix64_stream(seed: int, nwords: int) -> np.ndarray:
         z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M
         out[i] = z ^ (z >> 31)
     return out
+
+
+DIDX_MAGIC = bytes([28, 145, 78, 165, 25, 186, 179, 205])
+
+
+def didx_build(lengths, digests, uuid: bytes = b"\0" * 16, ctime: int = 0) -> bytes:
+    """PBS dynamic index image (restated from upstream pbs-datastore dynamic_index.rs / file_formats.rs;
+    UNVERIFIED against the Go module -- see oracle.c header): 4096-byte header {magic, uuid, ctime i64 LE,
+    index_csum = SHA-256 over the entry table, zero padding} + entries {u64 end LE, digest[32]}."""
+    body = bytearray()
+    end = 0
+    for ln, d in zip(lengths, digests):
+        end += int(ln)
+        body += end.to_bytes(8, "little") + bytes(d)
+    hdr = bytearray(4096)
+    hdr[0:8] = DIDX_MAGIC
+    hdr[8:24] = bytes(uuid).ljust(16, b"\0")[:16]
+    hdr[24:32] = int(ctime).to_bytes(8, "little", signed=True)
+    hdr[32:64] = hashlib.sha256(bytes(body)).digest()
+    return bytes(hdr) + bytes(body)

@@ -769,6 +769,68 @@ extern "C" int pbsgpu_set_seed_didx(pbsgpu_set *s, const uint8_t *didx, uint64_t
     return set_process(s, dig.data(), n, 1, nullptr);
 }
 
+// ---------------------------------------------------------------------------
+// f1: dynamic index images
+// ---------------------------------------------------------------------------
+static const uint8_t DIDX_MAGIC[8] = {28, 145, 78, 165, 25, 186, 179, 205};
+extern "C" int pbsgpu_sha256_batch(pbsgpu_ctx *, const void *, const uint64_t *, const uint64_t *, uint32_t, uint8_t *);
+
+extern "C" uint64_t pbsgpu_didx_size(uint64_t n) { return 4096 + n * 40; }
+
+extern "C" int pbsgpu_didx_build(pbsgpu_ctx *ctx, const pbsgpu_chunk *chunks, uint64_t n, const uint8_t uuid[16],
+                                 int64_t ctime, uint8_t *out, uint64_t cap) {
+    if (!ctx || (n && !chunks) || !out || !uuid) return PBSGPU_EINVAL;
+    if (cap < pbsgpu_didx_size(n)) return fail(ctx, PBSGPU_ERANGE, "didx buffer too small: %llu < %llu", (unsigned long long)cap, (unsigned long long)pbsgpu_didx_size(n));
+    memset(out, 0, 4096);
+    memcpy(out, DIDX_MAGIC, 8);
+    memcpy(out + 8, uuid, 16);
+    for (int i = 0; i < 8; i++) out[24 + i] = (uint8_t)((uint64_t)ctime >> (8 * i));
+    uint64_t total = 0, prev_end = 0;
+    uint32_t prev_stream = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        if (i == 0 || chunks[i].stream != prev_stream) prev_end = 0;
+        if (chunks[i].end_off < prev_end) return fail(ctx, PBSGPU_EINVAL, "chunk records not ordered by (stream, end_off) at %llu", (unsigned long long)i);
+        total += chunks[i].end_off - prev_end;
+        prev_end = chunks[i].end_off; prev_stream = chunks[i].stream;
+        uint8_t *e = out + 4096 + i * 40;
+        for (int k = 0; k < 8; k++) e[k] = (uint8_t)(total >> (8 * k));
+        memcpy(e + 8, chunks[i].digest, 32);
+    }
+    uint64_t off0 = 0, len0 = n * 40;
+    return pbsgpu_sha256_batch(ctx, out + 4096, &off0, &len0, 1, out + 32);   // index_csum (GPU)
+}
+
+extern "C" int pbsgpu_didx_parse(pbsgpu_ctx *ctx, const uint8_t *didx, uint64_t size, uint64_t *ends, uint8_t *digests,
+                                 uint64_t cap, uint64_t *n_entries, int verify) {
+    if (!didx || !n_entries) return PBSGPU_EINVAL;
+    if (size < 4096 || (size - 4096) % 40 || memcmp(didx, DIDX_MAGIC, 8) != 0)
+        return fail(ctx, PBSGPU_EINVAL, "not a dynamic index image");
+    uint64_t n = (size - 4096) / 40;
+    *n_entries = n;
+    if (ends || digests) {
+        if (cap < n) return fail(ctx, PBSGPU_ERANGE, "output capacity %llu < %llu entries", (unsigned long long)cap, (unsigned long long)n);
+        uint64_t prev = 0;
+        for (uint64_t i = 0; i < n; i++) {
+            const uint8_t *e = didx + 4096 + i * 40;
+            uint64_t end = 0;
+            for (int k = 0; k < 8; k++) end |= (uint64_t)e[k] << (8 * k);
+            if (end < prev) return fail(ctx, PBSGPU_EINVAL, "index offsets not monotonic at entry %llu", (unsigned long long)i);
+            prev = end;
+            if (ends) ends[i] = end;
+            if (digests) memcpy(digests + i * 32, e + 8, 32);
+        }
+    }
+    if (verify) {
+        if (!ctx) return PBSGPU_EINVAL;
+        uint8_t csum[32];
+        uint64_t off0 = 0, len0 = n * 40;
+        int rc = pbsgpu_sha256_batch(ctx, didx + 4096, &off0, &len0, 1, csum);
+        if (rc) return rc;
+        if (memcmp(csum, didx + 32, 32) != 0) return fail(ctx, PBSGPU_EINVAL, "index checksum mismatch");
+    }
+    return PBSGPU_OK;
+}
+
 // flags for chunk records that are already on the host, in order
 static int apply_set(pbsgpu_set *set, pbsgpu_chunk *out, uint64_t n) {
     if (!set || n == 0) return PBSGPU_OK;

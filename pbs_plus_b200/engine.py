@@ -170,6 +170,28 @@ class Engine:
                                              out.ctypes.data))
         return out
 
+    # -- f1: dynamic index images ---------------------------------------------------------
+    def didx_build(self, chunks: np.ndarray, uuid: bytes = b"\0" * 16, ctime: int = 0) -> bytes:
+        """Dynamic-index (.didx) image of chunk records in (stream, offset) order; offsets cumulative."""
+        rec = np.ascontiguousarray(chunks, dtype=CHUNK_DTYPE)
+        size = int(self._L.pbsgpu_didx_size(len(rec)))
+        out = np.zeros(size, dtype=np.uint8)
+        u = np.frombuffer(bytes(uuid).ljust(16, b"\0")[:16], dtype=np.uint8)
+        self._ck(self._L.pbsgpu_didx_build(self._h, rec.ctypes.data if len(rec) else None, len(rec), u.ctypes.data,
+                                           int(ctime), out.ctypes.data, size))
+        return out.tobytes()
+
+    def didx_parse(self, image: bytes, verify: bool = True):
+        """-> (ends u64[n], digests u8[n,32]); verify recomputes the index checksum on the GPU."""
+        a = np.frombuffer(image, dtype=np.uint8)
+        n = C.c_uint64()
+        self._ck(self._L.pbsgpu_didx_parse(self._h, a.ctypes.data, len(a), None, None, 0, C.byref(n), 0))
+        ends = np.zeros(n.value, dtype=np.uint64)
+        dig = np.zeros((n.value, 32), dtype=np.uint8)
+        self._ck(self._L.pbsgpu_didx_parse(self._h, a.ctypes.data, len(a), ends.ctypes.data, dig.ctypes.data, n.value,
+                                           C.byref(n), 1 if verify else 0))
+        return ends, dig
+
     # -- misc ---------------------------------------------------------------------------
     def digest_set(self, capacity_hint: int = 1 << 16) -> "DigestSet":
         return DigestSet(self, capacity_hint)

@@ -436,3 +436,26 @@ def test_all_long_chunks_take_the_latency_kernel(eng, torch):
         rec = eng.chunk_digest_batch(pg.make_config(avg), to_dev(torch, data), [0, 1_000_001], [1_000_001, 1_999_999])
         ref = oracle.chunk_digest_streams(oracle.config(avg), [data[:1_000_001], data[1_000_001:]])
         assert rec.tobytes() == ref.tobytes()
+
+
+def test_didx_image_build_parse_and_seed(eng, torch):
+    """f1: the dynamic-index image of a batch equals the oracle's (hashlib checksum), parses back, verifies,
+    rejects corruption, and seeds the known set."""
+    from oracle import pyref
+    arrs = [rnd(400_000, 81), rnd(0, 82), rnd(123_456, 83)]
+    buf, off, ln = pack(arrs)
+    rec = eng.chunk_digest_batch(pg.make_config(4096), to_dev(torch, buf), off, ln)
+    img = eng.didx_build(rec, uuid=bytes(range(16)), ctime=1_700_000_000)
+    lens = []
+    prev = {0: 0, 1: 0, 2: 0}
+    for r in rec:
+        lens.append(int(r["end_off"]) - prev[int(r["stream"])]); prev[int(r["stream"])] = int(r["end_off"])
+    assert img == pyref.didx_build(lens, [bytes(d) for d in rec["digest"]], bytes(range(16)), 1_700_000_000)
+    ends, dig = eng.didx_parse(img)
+    assert ends.tolist() == np.cumsum(lens).tolist() and (dig == rec["digest"]).all()
+    bad = bytearray(img); bad[4096 + 9] ^= 1
+    with pytest.raises(pg.PbsGpuError):
+        eng.didx_parse(bytes(bad))
+    s = eng.digest_set()
+    assert s.seed_didx(img) == len(rec) and s.probe(rec["digest"]).all()
+    assert len(eng.didx_parse(eng.didx_build(rec[:0]))[0]) == 0
