@@ -186,6 +186,16 @@ int pbsgpu_didx_build(pbsgpu_ctx *ctx, const pbsgpu_chunk *chunks, uint64_t n, c
 int pbsgpu_didx_parse(pbsgpu_ctx *ctx, const uint8_t *didx, uint64_t size, uint64_t *ends, uint8_t *digests,
                       uint64_t cap, uint64_t *n_entries, int verify);
 
+/* ---- f3 ("next" row): DataBlob checksums for NEW chunks ---------------------------------------
+ * A new chunk is uploaded as a PBS DataBlob { magic[8], crc32 LE of the payload, payload } (upstream
+ * pbs-datastore data_blob.rs; POST /dynamic_chunk, reference internal/server/backup/log_cleanup.go:19-31).
+ * pbsgpu_crc32_batch computes zlib-compatible CRC-32s of n byte ranges (HOST or DEVICE base) on the GPU;
+ * pbsgpu_blob_header fills the 12-byte header of an unencrypted, uncompressed blob.  zstd-compressed
+ * blobs are out of scope. */
+int pbsgpu_crc32_batch(pbsgpu_ctx *ctx, const void *base, const uint64_t *off, const uint64_t *len, uint32_t n,
+                       uint32_t *crc_out);
+void pbsgpu_blob_header(uint32_t crc, uint8_t out[12]);
+
 /* ---- pinned staging owned by C, filled by the Go side ----------------------------- */
 void *pbsgpu_host_alloc(pbsgpu_ctx *ctx, uint64_t bytes);
 void pbsgpu_host_free(pbsgpu_ctx *ctx, void *p);

@@ -88,6 +88,7 @@ struct pbsgpu_ctx {
     int variant = 0;
     // device copies of the chunker table (re-uploaded when the cfg table changes)
     uint32_t *d_table = nullptr, *d_rot = nullptr;
+    void *d_crc_tables = nullptr;   // K6 tables, uploaded on first use
     uint32_t table_cache[256];
     bool table_valid = false;
     pbsgpu_timing last_timing;
@@ -236,6 +237,7 @@ extern "C" void pbsgpu_close(pbsgpu_ctx *ctx) {
     for (int i = 0; i < N_STREAMS; i++) { cudaStreamDestroy(ctx->streams[i]); cudaStreamDestroy(ctx->streams2[i]); }
     cudaStreamDestroy(ctx->copy_stream);
     cudaFree(ctx->d_table); cudaFree(ctx->d_rot);
+    if (ctx->d_crc_tables) cudaFree(ctx->d_crc_tables);
     if (ctx->epoch) cudaEventDestroy(ctx->epoch);
     if (ctx->g_long || ctx->g_bulk) {
         auto gdestroy = driver_ep<CUresult (*)(CUgreenCtx)>("cuGreenCtxDestroy");
@@ -829,6 +831,64 @@ extern "C" int pbsgpu_didx_parse(pbsgpu_ctx *ctx, const uint8_t *didx, uint64_t 
         if (memcmp(csum, didx + 32, 32) != 0) return fail(ctx, PBSGPU_EINVAL, "index checksum mismatch");
     }
     return PBSGPU_OK;
+}
+
+// ---------------------------------------------------------------------------
+// f3: DataBlob checksums
+// ---------------------------------------------------------------------------
+static const uint8_t BLOB_MAGIC_UNCOMPRESSED[8] = {66, 171, 56, 7, 190, 131, 112, 161};
+
+extern "C" void pbsgpu_blob_header(uint32_t crc, uint8_t out[12]) {
+    memcpy(out, BLOB_MAGIC_UNCOMPRESSED, 8);
+    for (int i = 0; i < 4; i++) out[8 + i] = (uint8_t)(crc >> (8 * i));
+}
+
+extern "C" int pbsgpu_crc32_batch(pbsgpu_ctx *ctx, const void *base, const uint64_t *off, const uint64_t *len,
+                                  uint32_t n, uint32_t *crc_out) {
+    if (!ctx || (n && (!off || !len || !crc_out))) return PBSGPU_EINVAL;
+    Guard g(ctx);
+    if (n == 0) return PBSGPU_OK;
+    cudaStream_t st = ctx->streams[0];
+    if (!ctx->d_crc_tables) {
+        std::vector<uint8_t> h(crc_tables_bytes());
+        crc_fill_tables_host(h.data());
+        CK(cudaMalloc(&ctx->d_crc_tables, h.size()));
+        CK(cudaMemcpy(ctx->d_crc_tables, h.data(), h.size(), cudaMemcpyHostToDevice));
+    }
+    const uint64_t WB = crc_wb_bytes();
+    std::vector<uint64_t> wb_first(n + 1);
+    uint64_t total = 0, hi = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        wb_first[i] = total;
+        total += (len[i] + WB - 1) / WB;
+        hi = std::max(hi, off[i] + len[i]);
+    }
+    wb_first[n] = total;
+    const uint8_t *dbase = (const uint8_t *)base;
+    uint8_t *staged = nullptr;
+    if (hi && !is_device_ptr(base)) {
+        staged = (uint8_t *)ctx->dev.get(hi + 16);
+        if (!staged) return fail(ctx, PBSGPU_ENOMEM, "staging of %llu bytes failed", (unsigned long long)hi);
+        CK(cudaMemcpyAsync(staged, base, hi, cudaMemcpyHostToDevice, st));
+        dbase = staged;
+    }
+    uint64_t *d_off = (uint64_t *)ctx->dev.get(n * 8), *d_len = (uint64_t *)ctx->dev.get(n * 8);
+    uint64_t *d_first = (uint64_t *)ctx->dev.get((n + 1) * 8);
+    uint32_t *d_part = (uint32_t *)ctx->dev.get((total + 1) * 4), *d_out = (uint32_t *)ctx->dev.get((uint64_t)n * 4);
+    int rc = PBSGPU_OK;
+    if (!d_off || !d_len || !d_first || !d_part || !d_out) rc = fail(ctx, PBSGPU_ENOMEM, "device allocation failed");
+    else {
+        cudaError_t e = cudaMemcpyAsync(d_off, off, n * 8, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_len, len, n * 8, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_first, wb_first.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = launch_crc32(dbase, d_off, d_len, d_first, n, total, ctx->d_crc_tables, d_part, d_out, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(crc_out, d_out, (uint64_t)n * 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { (void)cudaGetLastError(); rc = fail(ctx, PBSGPU_ECUDA, "crc32 batch: %s", cudaGetErrorString(e)); }
+    }
+    ctx->dev.put(d_off); ctx->dev.put(d_len); ctx->dev.put(d_first); ctx->dev.put(d_part); ctx->dev.put(d_out);
+    ctx->dev.put(staged);
+    return rc;
 }
 
 // flags for chunk records that are already on the host, in order

@@ -102,6 +102,14 @@ cudaError_t launch_set_mark_probe_insert(SetTable t, const uint8_t *d32, const u
                                          uint8_t *is_rep_miss, unsigned long long *n_new, cudaStream_t st);
 cudaError_t launch_set_rehash(SetTable from, SetTable to, cudaStream_t st);
 
+// ---- CRC-32 (K6, DataBlob checksums) -----------------------------------------------------
+cudaError_t launch_crc32(const uint8_t *base, const uint64_t *off, const uint64_t *len, const uint64_t *wb_first,
+                         uint32_t n, uint64_t total_wb, const void *tables, uint32_t *part_crc, uint32_t *out,
+                         cudaStream_t st);
+size_t crc_tables_bytes();
+void crc_fill_tables_host(void *dst);
+uint64_t crc_wb_bytes();
+
 // ---- corpus (K5) ------------------------------------------------------------------
 cudaError_t launch_corpus_fill(const pbsgpu_corpus &c, uint64_t first_file, uint32_t n_files, uint8_t *dst,
                                uint64_t stride, cudaStream_t st);

@@ -170,6 +170,19 @@ class Engine:
                                              out.ctypes.data))
         return out
 
+    # -- f3: DataBlob checksums --------------------------------------------------------------
+    def crc32_batch(self, base, off, length) -> np.ndarray:
+        """zlib-compatible CRC-32 of n byte ranges (host or device base) on the GPU."""
+        o, l = self._offlen(off, length)
+        out = np.zeros(len(o), dtype=np.uint32)
+        self._ck(self._L.pbsgpu_crc32_batch(self._h, _ptr(base), o.ctypes.data, l.ctypes.data, len(o), out.ctypes.data))
+        return out
+
+    def blob_header(self, crc: int) -> bytes:
+        out = np.zeros(12, dtype=np.uint8)
+        self._L.pbsgpu_blob_header(int(crc), out.ctypes.data)
+        return out.tobytes()
+
     # -- f1: dynamic index images ---------------------------------------------------------
     def didx_build(self, chunks: np.ndarray, uuid: bytes = b"\0" * 16, ctime: int = 0) -> bytes:
         """Dynamic-index (.didx) image of chunk records in (stream, offset) order; offsets cumulative."""

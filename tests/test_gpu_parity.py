@@ -459,3 +459,19 @@ def test_didx_image_build_parse_and_seed(eng, torch):
     s = eng.digest_set()
     assert s.seed_didx(img) == len(rec) and s.probe(rec["digest"]).all()
     assert len(eng.didx_parse(eng.didx_build(rec[:0]))[0]) == 0
+
+
+def test_crc32_batch_matches_zlib(eng, torch):
+    """f3: DataBlob payload checksums.  zlib.crc32 is the (authoritative) oracle."""
+    import zlib
+    data = rnd(3_000_000, 91)
+    offs, lens = [], []
+    for n in [0, 1, 2, 3, 4, 5, 7, 8, 63, 4095, 4096, 4097, 8191, 131071, 131072, 131073, 262144, 1_000_003, 2_500_000]:
+        for a in (0, 1, 2, 3, 17):
+            offs.append(a); lens.append(n)
+    for host in (True, False):
+        crc = eng.crc32_batch(data if host else to_dev(torch, data), offs, lens)
+        for o, n, c in zip(offs, lens, crc):
+            assert int(c) == zlib.crc32(data[o:o + n].tobytes()), (o, n, host)
+    hdr = eng.blob_header(int(crc[-1]))
+    assert hdr[:8] == bytes([66, 171, 56, 7, 190, 131, 112, 161]) and int.from_bytes(hdr[8:], "little") == int(crc[-1])
