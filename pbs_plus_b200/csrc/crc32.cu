@@ -86,12 +86,20 @@ __global__ void __launch_bounds__(256) k_crc32_blocks(const uint8_t *base, const
     uint32_t seg = done >= rlen ? 0u : (rlen - done < (uint64_t)CRC_SEG ? (uint32_t)(rlen - done) : (uint32_t)CRC_SEG);
     uint32_t c = 0xffffffffu;
     uint32_t i = 0;
-    const uint32_t mis = (uint32_t)((uintptr_t)p & 3);
-    if (mis) for (; i < seg && i < 4 - mis; i++) c = T[0][(c ^ p[i]) & 0xff] ^ (c >> 8);   // to 4 B alignment
-    for (; i + 4 <= seg; i += 4) {
-        c ^= __ldg((const uint32_t *)(p + i));
-        c = T[3][c & 0xff] ^ T[2][(c >> 8) & 0xff] ^ T[1][(c >> 16) & 0xff] ^ T[0][c >> 24];
+    const uint32_t mis = (uint32_t)((uintptr_t)p & 15);
+    if (mis) for (; i < seg && i < 16 - mis; i++) c = T[0][(c ^ p[i]) & 0xff] ^ (c >> 8);   // to 16 B alignment
+#define CRC_WORD(w) do { c ^= (w); c = T[3][c & 0xff] ^ T[2][(c >> 8) & 0xff] ^ T[1][(c >> 16) & 0xff] ^ T[0][c >> 24]; } while (0)
+    // 16-byte loads: every lane touches its own cache line, so the L1 cost is per instruction, not per byte
+    for (; i + 64 <= seg; i += 64) {
+        uint4 v0 = __ldg((const uint4 *)(p + i)), v1 = __ldg((const uint4 *)(p + i + 16));
+        uint4 v2 = __ldg((const uint4 *)(p + i + 32)), v3 = __ldg((const uint4 *)(p + i + 48));
+        CRC_WORD(v0.x); CRC_WORD(v0.y); CRC_WORD(v0.z); CRC_WORD(v0.w);
+        CRC_WORD(v1.x); CRC_WORD(v1.y); CRC_WORD(v1.z); CRC_WORD(v1.w);
+        CRC_WORD(v2.x); CRC_WORD(v2.y); CRC_WORD(v2.z); CRC_WORD(v2.w);
+        CRC_WORD(v3.x); CRC_WORD(v3.y); CRC_WORD(v3.z); CRC_WORD(v3.w);
     }
+    for (; i + 4 <= seg; i += 4) CRC_WORD(__ldg((const uint32_t *)(p + i)));
+#undef CRC_WORD
     for (; i < seg; i++) c = T[0][(c ^ p[i]) & 0xff] ^ (c >> 8);
     c = ~c;                       // standard CRC of this lane's segment (crc of empty = 0)
     if (seg == 0) c = 0;
