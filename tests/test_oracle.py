@@ -69,6 +69,11 @@ def test_default_table_fingerprint():
     # fingerprint a maintainer can diff against the Go module's table (little-endian u32s)
     fp = hashlib.sha256(t.astype("<u4").tobytes()).hexdigest()
     assert fp == json.loads((GOLDEN / "table_fingerprint.json").read_text())["sha256_le_u32"]
+    # Internal evidence that the recalled table is the genuine casync/PBS one: that table is bit-balanced
+    # (every bit column holds exactly 128 ones, so the XOR of all entries is 0 -- what makes buzhash
+    # uniform).  A single mis-transcribed entry would break this with overwhelming probability.
+    bits = ((t[:, None] >> np.arange(32, dtype=np.uint32)[None, :]) & 1).sum(axis=0)
+    assert (bits == 128).all() and int(np.bitwise_xor.reduce(t)) == 0
 
 
 def test_rolling_equals_closed_form_window():
