@@ -332,7 +332,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
 
 def run_cfg3(args):
     """BASELINE config[2]: a 10 TB synthetic corpus with 30 % duplicate 4 MiB blocks (runs of 8), streamed
-    through HBM in 64 GiB batches generated on the device; reports throughput and the digest-set hit rate.
+    through HBM in 16 GiB batches (6 in flight) generated on the device; reports throughput and the hit rate.
     Not the default bench line (diagnostic / parity-at-scale run; see profiles/)."""
     import torch
 
@@ -340,16 +340,18 @@ def run_cfg3(args):
 
     torch.cuda.set_device(0)
     eng = pg.Engine(0, profiling=False)
-    file_len, n_files = args.file_mib << 20, args.files
+    file_len = args.file_mib << 20
+    n_files = min(args.files, 256)                 # 16 GiB batches, NBUF of them in flight
+    NBUF = 6
     total = int(args.total_tb * 1e12)
     n_batches = max(1, total // (n_files * file_len))
     corp = pg.corpus(seed=3, file_len=file_len, block_len=4 << 20, run_blocks=8, dup_permille=300)
     cfg = pg.buzhash.NewConfig(4096)
     known = eng.digest_set(4 << 20)
-    bufs = [torch.empty(n_files * file_len, dtype=torch.uint8, device="cuda") for _ in range(2)]
+    bufs = [torch.empty(n_files * file_len, dtype=torch.uint8, device="cuda") for _ in range(NBUF)]
     off = np.arange(n_files, dtype=np.uint64) * file_len
     ln = np.full(n_files, file_len, dtype=np.uint64)
-    jobs = [None, None]
+    jobs = [None] * NBUF
     chunks = hits = 0
     gen_s = 0.0
 
@@ -364,13 +366,14 @@ def run_cfg3(args):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for b in range(n_batches):
-        slot = b & 1
-        drain(slot)
+        slot = b % NBUF
+        drain(slot)                                # in order: the set sees batches in corpus order
         g0 = time.perf_counter()
         eng.corpus_fill(corp, b * n_files, n_files, bufs[slot], file_len)
         gen_s += time.perf_counter() - g0
         jobs[slot] = eng.submit(cfg, bufs[slot], off, ln)
-    drain(0); drain(1)
+    for k in range(NBUF):
+        drain((n_batches + k) % NBUF)
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     nbytes = n_batches * n_files * file_len

@@ -52,26 +52,29 @@ __device__ __forceinline__ uint64_t edit_word(const pbsgpu_corpus &c, uint64_t g
     return v;
 }
 
-// grid.y = file, grid.x * block covers the words of one file
+// grid.y = file, grid.x = corpus block (duplicate granule) of that file; the block's seed is resolved
+// once per thread (two 64-bit divisions and a hash chain), then the thread strides over the words.
 __global__ void __launch_bounds__(256) k_corpus_fill(pbsgpu_corpus c, uint64_t first_file, uint8_t *dst, uint64_t stride) {
-    const uint64_t words_per_file = (c.file_len + 7) / 8;
     const uint64_t words_per_block = c.block_len / 8;
     const uint64_t bpf = (c.file_len + c.block_len - 1) / c.block_len;
     const uint64_t file = first_file + blockIdx.y;
     uint8_t *out = dst + (uint64_t)blockIdx.y * stride;
-    for (uint64_t wi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; wi < words_per_file;
-         wi += (uint64_t)gridDim.x * blockDim.x) {
-        uint64_t bi = wi / words_per_block, w = wi - bi * words_per_block;
-        uint64_t gblock = file * bpf + bi;
-        uint64_t cb = canonical_block(c, gblock);
-        uint64_t bseed = fmix64(c.seed * 0xA0761D6478BD642FULL + cb * 0xE7037ED1A0B428DBULL + 0x1234567ULL);
-        uint64_t v = fmix64(bseed + (w + 1) * GOLD);
-        if (c.edit_mode) v = edit_word(c, gblock, w, v);
-        uint64_t byte_off = wi * 8;
-        if (byte_off + 8 <= c.file_len) {
-            *(uint64_t *)(out + byte_off) = v;
-        } else {
-            for (uint64_t j = 0; byte_off + j < c.file_len; j++) out[byte_off + j] = (uint8_t)(v >> (8 * j));
+    for (uint64_t bi = blockIdx.x; bi < bpf; bi += gridDim.x) {
+        const uint64_t gblock = file * bpf + bi;
+        const uint64_t cb = canonical_block(c, gblock);
+        const uint64_t bseed = fmix64(c.seed * 0xA0761D6478BD642FULL + cb * 0xE7037ED1A0B428DBULL + 0x1234567ULL);
+        const uint64_t block_off = bi * c.block_len;
+        const uint64_t remain = c.file_len - block_off;
+        const uint64_t nwords = remain >= c.block_len ? words_per_block : (remain + 7) / 8;
+        for (uint64_t w = threadIdx.x; w < nwords; w += blockDim.x) {
+            uint64_t v = fmix64(bseed + (w + 1) * GOLD);
+            if (c.edit_mode) v = edit_word(c, gblock, w, v);
+            const uint64_t byte_off = block_off + w * 8;
+            if (byte_off + 8 <= c.file_len) {
+                *(uint64_t *)(out + byte_off) = v;
+            } else {
+                for (uint64_t j = 0; byte_off + j < c.file_len; j++) out[byte_off + j] = (uint8_t)(v >> (8 * j));
+            }
         }
     }
 }
@@ -79,9 +82,8 @@ __global__ void __launch_bounds__(256) k_corpus_fill(pbsgpu_corpus c, uint64_t f
 cudaError_t launch_corpus_fill(const pbsgpu_corpus &c, uint64_t first_file, uint32_t n_files, uint8_t *dst,
                                uint64_t stride, cudaStream_t st) {
     if (n_files == 0 || c.file_len == 0) return cudaSuccess;
-    uint64_t words = (c.file_len + 7) / 8;
-    uint64_t bx = (words + 255) / 256;
-    if (bx > 4096) bx = 4096;
+    uint64_t bpf = (c.file_len + c.block_len - 1) / c.block_len;
+    uint64_t bx = bpf > 65535 ? 65535 : bpf;
     for (uint32_t f0 = 0; f0 < n_files; f0 += 65535) {
         uint32_t nf = n_files - f0 < 65535 ? n_files - f0 : 65535;
         dim3 grid((unsigned)bx, nf);
