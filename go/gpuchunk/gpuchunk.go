@@ -178,3 +178,45 @@ func (b *Batch) Flush(known *KnownSet) ([]Chunk, error) {
 }
 
 func (b *Batch) Close() { C.pbsgpu_host_free(b.e.ctx, b.buf) }
+
+// BuildDidx renders the dynamic-index image (<name>.ppxar.didx, commit.go:321-322) for chunks in
+// (stream, offset) order; offsets are cumulative over the archive stream, the checksum is computed on the GPU.
+func (e *Engine) BuildDidx(chunks []Chunk, uuid [16]byte, ctime int64) ([]byte, error) {
+	n := len(chunks)
+	rec := make([]C.pbsgpu_chunk, n+1)
+	for i, c := range chunks {
+		rec[i].stream = C.uint32_t(c.Stream)
+		rec[i].end_off = C.uint64_t(c.End)
+		for k := 0; k < 32; k++ {
+			rec[i].digest[k] = C.uint8_t(c.Digest[k])
+		}
+	}
+	out := make([]byte, uint64(C.pbsgpu_didx_size(C.uint64_t(n))))
+	rc := C.pbsgpu_didx_build(e.ctx, &rec[0], C.uint64_t(n), (*C.uint8_t)(unsafe.Pointer(&uuid[0])), C.int64_t(ctime),
+		(*C.uint8_t)(unsafe.Pointer(&out[0])), C.uint64_t(len(out)))
+	return out, e.err(rc)
+}
+
+// BlobCRC32 returns the DataBlob payload checksums of ranges [off[i], off[i]+len[i]) of the batch's pinned
+// staging buffer (only NEW chunks need a blob; POST /dynamic_chunk).
+func (b *Batch) BlobCRC32(off, length []uint64) ([]uint32, error) {
+	n := len(off)
+	if n == 0 {
+		return nil, nil
+	}
+	o := make([]C.uint64_t, n)
+	l := make([]C.uint64_t, n)
+	for i := range off {
+		o[i], l[i] = C.uint64_t(off[i]), C.uint64_t(length[i])
+	}
+	crc := make([]C.uint32_t, n)
+	rc := C.pbsgpu_crc32_batch(b.e.ctx, b.buf, &o[0], &l[0], C.uint32_t(n), &crc[0])
+	if err := b.e.err(rc); err != nil {
+		return nil, err
+	}
+	res := make([]uint32, n)
+	for i := range crc {
+		res[i] = uint32(crc[i])
+	}
+	return res, nil
+}

@@ -68,3 +68,32 @@ def test_product_never_imports_the_oracle():
             txt = p.read_text()
             assert "import oracle" not in txt and "from oracle" not in txt, p
             assert '#include "../../oracle' not in txt and "liboracle" not in txt, p
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: pbsgpu.h must compile as C11 (what cgo feeds to its C compiler) and a C
+    program must link against the library and call the host-only entry points."""
+    import subprocess
+    src = tmp_path / "t.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include "pbsgpu.h"
+int main(void) {
+    pbsgpu_cfg c;
+    if (pbsgpu_config_kib(4096, NULL, &c) != 0) return 1;
+    if (c.avg != (4u << 20) || c.min != (1u << 20) || c.max != (16u << 20) || c.mask != 0x7FFFFFu) return 2;
+    if (pbsgpu_config(3000, NULL, &c) != PBSGPU_EINVAL) return 3;
+    if (pbsgpu_default_table()[0] != 0x458be752u) return 4;
+    if (pbsgpu_didx_size(10) != 4096 + 400) return 5;
+    unsigned char h[12]; pbsgpu_blob_header(0x11223344u, h);
+    if (h[0] != 66 || h[8] != 0x44 || h[11] != 0x11) return 6;
+    printf("version %d\n", pbsgpu_version());
+    return 0;
+}
+''')
+    exe = tmp_path / "t.bin"
+    lib = ROOT / "pbs_plus_b200"
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Werror", "-I", str(ROOT / "include"), "-o", str(exe), str(src),
+                           f"-L{lib}", "-lpbsgpu", f"-Wl,-rpath,{lib}"])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip() == "version 100", (out.returncode, out.stdout, out.stderr)
