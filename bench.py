@@ -332,7 +332,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
 
 def run_cfg3(args):
     """BASELINE config[2]: a 10 TB synthetic corpus with 30 % duplicate 4 MiB blocks (runs of 8), streamed
-    through HBM in 16 GiB batches (6 in flight) generated on the device; reports throughput and the hit rate.
+    through HBM in 32 GiB batches (3 in flight) generated on the device; reports throughput and the hit rate.
     Not the default bench line (diagnostic / parity-at-scale run; see profiles/)."""
     import torch
 
@@ -341,8 +341,8 @@ def run_cfg3(args):
     torch.cuda.set_device(0)
     eng = pg.Engine(0, profiling=False)
     file_len = args.file_mib << 20
-    n_files = min(args.files, 256)                 # 16 GiB batches, NBUF of them in flight
-    NBUF = 6
+    n_files = min(args.files, 512)                 # 32 GiB batches, NBUF of them in flight
+    NBUF = 3
     total = int(args.total_tb * 1e12)
     n_batches = max(1, total // (n_files * file_len))
     corp = pg.corpus(seed=3, file_len=file_len, block_len=4 << 20, run_blocks=8, dup_permille=300)

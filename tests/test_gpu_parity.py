@@ -475,3 +475,21 @@ def test_crc32_batch_matches_zlib(eng, torch):
             assert int(c) == zlib.crc32(data[o:o + n].tobytes()), (o, n, host)
     hdr = eng.blob_header(int(crc[-1]))
     assert hdr[:8] == bytes([66, 171, 56, 7, 190, 131, 112, 161]) and int.from_bytes(hdr[8:], "little") == int(crc[-1])
+
+
+def test_cfg1_single_1gib_stream(eng, torch):
+    """BASELINE config[0]: ONE 1 GiB synthetic stream, 4 MiB average -- the case the reference's CPU chunker
+    runs.  Cut-for-cut and digest-for-digest against the oracle (single thread, SHA-NI)."""
+    n = 1 << 30
+    dev = torch.empty(n, dtype=torch.uint8, device="cuda")
+    eng.corpus_fill(pg.corpus(seed=1, file_len=n), 0, 1, dev, n)
+    rec = eng.chunk_digest_batch(pg.buzhash.NewConfig(4096), dev, [0], [n])
+    ref = oracle.chunk_digest(oracle.config(4 << 20), oracle.corpus_file(oracle.corpus(seed=1, file_len=n), 0))
+    assert rec.tobytes() == ref.tobytes() and 200 < len(rec) < 400 and int(rec["end_off"][-1]) == n
+    # the same stream through the streaming form (state carried across 64 MiB writes)
+    host = dev.cpu().numpy()
+    st = eng.stream(pg.buzhash.NewConfig(4096))
+    for i in range(0, n, 64 << 20):
+        st.write(host[i:i + (64 << 20)])
+    assert st.finish().tobytes() == ref.tobytes()
+    st.close()
