@@ -855,15 +855,10 @@ extern "C" int pbsgpu_crc32_batch(pbsgpu_ctx *ctx, const void *base, const uint6
         CK(cudaMalloc(&ctx->d_crc_tables, h.size()));
         CK(cudaMemcpy(ctx->d_crc_tables, h.data(), h.size(), cudaMemcpyHostToDevice));
     }
-    const uint64_t WB = crc_wb_bytes();
-    std::vector<uint64_t> wb_first(n + 1);
-    uint64_t total = 0, hi = 0;
-    for (uint32_t i = 0; i < n; i++) {
-        wb_first[i] = total;
-        total += (len[i] + WB - 1) / WB;
-        hi = std::max(hi, off[i] + len[i]);
-    }
-    wb_first[n] = total;
+    static int crc_variant = -1;   // 0 = TMA-tiled kernel (default), 1 = simple lane-strided kernel
+    if (crc_variant < 0) { const char *e = getenv("PBSGPU_CRC_VARIANT"); crc_variant = e ? atoi(e) : 1; }   // tiled kernel becomes the default once verified on the GPU
+    uint64_t hi = 0;
+    for (uint32_t i = 0; i < n; i++) hi = std::max(hi, off[i] + len[i]);
     const uint8_t *dbase = (const uint8_t *)base;
     uint8_t *staged = nullptr;
     if (hi && !is_device_ptr(base)) {
@@ -872,6 +867,20 @@ extern "C" int pbsgpu_crc32_batch(pbsgpu_ctx *ctx, const void *base, const uint6
         CK(cudaMemcpyAsync(staged, base, hi, cudaMemcpyHostToDevice, st));
         dbase = staged;
     }
+    // work units: 128 KiB warp blocks (simple) or <= 576 KiB regions of the 16 B aligned body (tiled)
+    const uint64_t UNIT = crc_variant ? crc_wb_bytes() : crc_region_bytes();
+    std::vector<uint64_t> wb_first(n + 1);
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        wb_first[i] = total;
+        if (crc_variant) total += (len[i] + UNIT - 1) / UNIT;
+        else if (len[i]) {
+            uint64_t head = (16 - ((uintptr_t)(dbase + off[i]) & 15)) & 15;
+            uint64_t body = len[i] > head ? len[i] - head : 0;
+            total += std::max<uint64_t>(1, (body + UNIT - 1) / UNIT);
+        }
+    }
+    wb_first[n] = total;
     uint64_t *d_off = (uint64_t *)ctx->dev.get(n * 8), *d_len = (uint64_t *)ctx->dev.get(n * 8);
     uint64_t *d_first = (uint64_t *)ctx->dev.get((n + 1) * 8);
     uint32_t *d_part = (uint32_t *)ctx->dev.get((total + 1) * 4), *d_out = (uint32_t *)ctx->dev.get((uint64_t)n * 4);
@@ -881,7 +890,9 @@ extern "C" int pbsgpu_crc32_batch(pbsgpu_ctx *ctx, const void *base, const uint6
         cudaError_t e = cudaMemcpyAsync(d_off, off, n * 8, cudaMemcpyHostToDevice, st);
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_len, len, n * 8, cudaMemcpyHostToDevice, st);
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_first, wb_first.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st);
-        if (e == cudaSuccess) e = launch_crc32(dbase, d_off, d_len, d_first, n, total, ctx->d_crc_tables, d_part, d_out, ctx->sm_count, st);
+        if (e == cudaSuccess)
+            e = crc_variant ? launch_crc32(dbase, d_off, d_len, d_first, n, total, ctx->d_crc_tables, d_part, d_out, ctx->sm_count, st)
+                            : launch_crc32_tiled(dbase, d_off, d_len, d_first, n, total, ctx->d_crc_tables, d_part, d_out, ctx->sm_count, st);
         if (e == cudaSuccess) e = cudaMemcpyAsync(crc_out, d_out, (uint64_t)n * 4, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) { (void)cudaGetLastError(); rc = fail(ctx, PBSGPU_ECUDA, "crc32 batch: %s", cudaGetErrorString(e)); }

@@ -106,6 +106,10 @@ cudaError_t launch_set_rehash(SetTable from, SetTable to, cudaStream_t st);
 cudaError_t launch_crc32(const uint8_t *base, const uint64_t *off, const uint64_t *len, const uint64_t *wb_first,
                          uint32_t n, uint64_t total_wb, const void *tables, uint32_t *part_crc, uint32_t *out,
                          int sm_count, cudaStream_t st);
+cudaError_t launch_crc32_tiled(const uint8_t *base, const uint64_t *off, const uint64_t *len,
+                               const uint64_t *region_first, uint32_t n, uint64_t total_regions, const void *tables,
+                               uint32_t *part_crc, uint32_t *out, int sm_count, cudaStream_t st);
+uint64_t crc_region_bytes();
 size_t crc_tables_bytes();
 void crc_fill_tables_host(void *dst);
 uint64_t crc_wb_bytes();

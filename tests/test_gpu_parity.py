@@ -466,8 +466,9 @@ def test_crc32_batch_matches_zlib(eng, torch):
     import zlib
     data = rnd(3_000_000, 91)
     offs, lens = [], []
-    for n in [0, 1, 2, 3, 4, 5, 7, 8, 63, 4095, 4096, 4097, 8191, 131071, 131072, 131073, 262144, 1_000_003, 2_500_000]:
-        for a in (0, 1, 2, 3, 17):
+    for n in [0, 1, 2, 3, 4, 5, 7, 8, 15, 16, 17, 63, 143, 144, 145, 4095, 4096, 4097, 4607, 4608, 4609, 8191, 131071,
+              131072, 131073, 262144, 589823, 589824, 589825, 1_000_003, 2_500_000]:
+        for a in (0, 1, 2, 3, 15, 16, 17):
             offs.append(a); lens.append(n)
     for host in (True, False):
         crc = eng.crc32_batch(data if host else to_dev(torch, data), offs, lens)
