@@ -856,7 +856,7 @@ extern "C" int pbsgpu_crc32_batch(pbsgpu_ctx *ctx, const void *base, const uint6
         CK(cudaMemcpy(ctx->d_crc_tables, h.data(), h.size(), cudaMemcpyHostToDevice));
     }
     static int crc_variant = -1;   // 0 = TMA-tiled kernel (default), 1 = simple lane-strided kernel
-    if (crc_variant < 0) { const char *e = getenv("PBSGPU_CRC_VARIANT"); crc_variant = e ? atoi(e) : 1; }   // tiled kernel becomes the default once verified on the GPU
+    if (crc_variant < 0) { const char *e = getenv("PBSGPU_CRC_VARIANT"); crc_variant = e ? atoi(e) : 0; }
     uint64_t hi = 0;
     for (uint32_t i = 0; i < n; i++) hi = std::max(hi, off[i] + len[i]);
     const uint8_t *dbase = (const uint8_t *)base;
