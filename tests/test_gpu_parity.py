@@ -494,3 +494,29 @@ def test_cfg1_single_1gib_stream(eng, torch):
         st.write(host[i:i + (64 << 20)])
     assert st.finish().tobytes() == ref.tobytes()
     st.close()
+
+
+@pytest.mark.parametrize("env", [{"PBSGPU_PARTITION_SMS": "0"}, {"PBSGPU_PARTITION_SMS": "0", "PBSGPU_SHA_HYBRID": "2"},
+                                 {"PBSGPU_PARTITION_SMS": "16"}])
+def test_results_do_not_depend_on_the_sm_partition(torch, env):
+    """No green contexts (fallback), forced hybrid launch without a partition, and another partition size:
+    same chunks, same digests."""
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        e = pg.Engine(0)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                del os.environ[k]
+            else:
+                os.environ[k] = v
+    try:
+        if env["PBSGPU_PARTITION_SMS"] == "0":
+            assert e.partition_info() == (0, 0)
+        arrs = [rnd(3_000_000, 700), rnd(10, 701), rnd(1_234_567, 702)]
+        buf, off, ln = pack(arrs)
+        rec = e.chunk_digest_batch(pg.make_config(1 << 16), to_dev(torch, buf), off, ln)
+        assert rec.tobytes() == oracle.chunk_digest_streams(oracle.config(1 << 16), arrs).tobytes()
+    finally:
+        e.close()
