@@ -506,7 +506,9 @@ static int job_enqueue_back(pbsgpu_job *j) {
             cudaStream_t side = serial ? st : j->st2;
             uint64_t thr64 = (uint64_t)j->cfg.avg * (uint64_t)thr_x10 / 10;
             uint32_t thr = thr64 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)thr64;
-            CK(launch_split_point(j->d_keys2, &j->d_counters[1], j->chunk_cap, thr, &j->d_counters[2], st));
+            // at most one latency CTA (32 chunks) per SM of the partition and job; the longest chunks first
+            const unsigned long long max_head = 32ull * (unsigned long long)(ctx->part_sms > 0 ? ctx->part_sms : 24);
+            CK(launch_split_point(j->d_keys2, &j->d_counters[1], j->chunk_cap, thr, max_head, &j->d_counters[2], st));
             CK(cudaEventRecord(j->ev[EV_FORK], st));
             if (!serial) CK(cudaStreamWaitEvent(side, j->ev[EV_FORK], 0));
             ha.n_head = &j->d_counters[2];

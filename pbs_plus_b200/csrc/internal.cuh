@@ -83,7 +83,8 @@ cudaError_t launch_sha_simple(const ShaArgs &a, cudaStream_t st);
 cudaError_t launch_sha_tuned(const ShaArgs &a, int sm_count, cudaStream_t st);   // throughput kernel
 cudaError_t launch_sha_split(const ShaArgs &a, cudaStream_t st);                 // latency kernel
 cudaError_t launch_split_point(const uint32_t *len_sorted_desc, const unsigned long long *n_chunks, uint64_t cap,
-                               uint32_t threshold, unsigned long long *n_head, cudaStream_t st);
+                               uint32_t threshold, unsigned long long max_head, unsigned long long *n_head,
+                               cudaStream_t st);
 int sha_hybrid_enabled();
 cudaError_t launch_len_keys(const ChunkRef *chunks, const unsigned long long *n_chunks, uint64_t cap,
                             uint32_t *keys, uint32_t *vals, cudaStream_t st);

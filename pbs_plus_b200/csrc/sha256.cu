@@ -470,9 +470,12 @@ cudaError_t launch_sha_split(const ShaArgs &a, cudaStream_t st) {
     }
 }
 
-// number of leading entries (lengths sorted descending) longer than `threshold`, rounded up to 32
+// number of leading entries (lengths sorted descending) longer than `threshold`, rounded up to 32 and
+// capped at `max_head`: the latency partition is small, so when most chunks are long (zero-filled or
+// otherwise structured data cuts every chunk at max) only the longest ones go there and the rest stays
+// with the throughput kernel on the big partition
 __global__ void k_split_point(const uint32_t *len_sorted_desc, const unsigned long long *n_chunks, uint64_t cap,
-                              uint32_t threshold, unsigned long long *n_head) {
+                              uint32_t threshold, unsigned long long max_head, unsigned long long *n_head) {
     unsigned long long n = *n_chunks;
     if (n > cap) n = cap;
     unsigned long long lo = 0, hi = n;     // first index with len <= threshold
@@ -481,11 +484,13 @@ __global__ void k_split_point(const uint32_t *len_sorted_desc, const unsigned lo
         if (len_sorted_desc[mid] > threshold) lo = mid + 1; else hi = mid;
     }
     unsigned long long h = (lo + 31) & ~31ull;
+    if (h > max_head) h = max_head & ~31ull;
     *n_head = h > n ? n : h;
 }
 cudaError_t launch_split_point(const uint32_t *len_sorted_desc, const unsigned long long *n_chunks, uint64_t cap,
-                               uint32_t threshold, unsigned long long *n_head, cudaStream_t st) {
-    k_split_point<<<1, 1, 0, st>>>(len_sorted_desc, n_chunks, cap, threshold, n_head);
+                               uint32_t threshold, unsigned long long max_head, unsigned long long *n_head,
+                               cudaStream_t st) {
+    k_split_point<<<1, 1, 0, st>>>(len_sorted_desc, n_chunks, cap, threshold, max_head, n_head);
     return cudaGetLastError();
 }
 

@@ -520,3 +520,14 @@ def test_results_do_not_depend_on_the_sm_partition(torch, env):
         assert rec.tobytes() == oracle.chunk_digest_streams(oracle.config(1 << 16), arrs).tobytes()
     finally:
         e.close()
+
+
+def test_mostly_long_chunks_are_capped_for_the_latency_partition(eng, torch):
+    """Zero-filled data cuts every chunk at max: far more 'long' chunks than the latency partition should take.
+    The head is capped (longest first); results stay exact."""
+    n = 96 << 20
+    data = np.zeros(n, dtype=np.uint8)
+    data[5::1_000_003] = 1
+    rec = eng.chunk_digest_batch(pg.make_config(4096), to_dev(torch, data), [0], [n])     # 6144 chunks of 16 KiB
+    assert len(rec) > 24 * 32 * 4
+    assert rec.tobytes() == oracle.chunk_digest(oracle.config(4096), data).tobytes()
