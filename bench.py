@@ -309,11 +309,25 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                                                         "sha_bulk_ms", "total_ms")},
         },
     }
+    del data
+    torch.cuda.empty_cache()
+    if not args.no_e2e:
+        # every rank runs the host-buffer path on its own GPU / PCIe link (rank r hashes its own files);
+        # whole-job e2e = bytes of all ranks / slowest rank's time
+        e2e = run_e2e(args, eng, cfg, pg, torch, first_file=rank * args.e2e_files)
+        if world > 1:
+            sec = torch.tensor([e2e.get("seconds") or 1e30], dtype=torch.float64, device=dev_t)
+            dist.all_reduce(sec, op=dist.ReduceOp.MAX)
+            if e2e.get("value") is not None and float(sec.item()) < 1e29:
+                e2e["value"] = world * e2e["h2d_bytes_per_step"] * e2e["steps"] / float(sec.item()) / GIB
+                e2e["h2d_bytes_per_step"] *= world
+                e2e["d2h_bytes_per_step"] *= world
+                e2e["seconds"] = float(sec.item())
+                e2e["workload"] += f"; x{world} ranks, max over ranks"
+            else:
+                e2e = {"value": None, "unit": "GiB/s", "error": "a rank could not run the host-buffer path"}
+        out["e2e"] = e2e
     if rank == 0:
-        del data
-        torch.cuda.empty_cache()
-        if not args.no_e2e:
-            out["e2e"] = run_e2e(args, eng, cfg, pg, torch)
         if not args.no_cpu:
             cores = os.cpu_count() or 1
             n_s = max(cores, min(2 * cores, (8 << 30) // file_len))
@@ -386,7 +400,7 @@ def run_cfg3(args):
     eng.close()
 
 
-def run_e2e(args, eng, cfg, pg, torch):
+def run_e2e(args, eng, cfg, pg, torch, first_file=0):
     """Same metric through the public C-ABI call with HOST buffers: every step is one blocking
     pbsgpu_chunk_digest_batch call that copies that step's inputs from pinned host memory to the device
     (staged in 4 GiB groups, overlapped with the kernels) and returns the chunk records to the host.
@@ -404,7 +418,7 @@ def run_e2e(args, eng, cfg, pg, torch):
         return {"value": None, "unit": "GiB/s", "error": str(e)}
     # fill the pinned buffer with the same corpus (generated on the device, copied back once, untimed)
     tmp = torch.empty(n * file_len, dtype=torch.uint8, device="cuda")
-    eng.corpus_fill(pg.corpus(seed=2, file_len=file_len), 0, n, tmp, file_len)
+    eng.corpus_fill(pg.corpus(seed=2, file_len=file_len), first_file, n, tmp, file_len)
     torch.from_numpy(np.asarray(host)).copy_(tmp)
     del tmp
     torch.cuda.empty_cache()
@@ -441,7 +455,7 @@ def run_e2e(args, eng, cfg, pg, torch):
     if errs:
         return {"value": None, "unit": "GiB/s", "error": errs[0]}
     return {"value": n * file_len * steps / dt / GIB, "unit": "GiB/s", "h2d_bytes_per_step": int(n * file_len),
-            "d2h_bytes_per_step": int(nrec[0] * 48), "steps": steps, "host_threads": workers,
+            "d2h_bytes_per_step": int(nrec[0] * 48), "steps": steps, "host_threads": workers, "seconds": dt,
             "workload": f"{n} x {args.file_mib} MiB files of the cfg2 corpus per step (one blocking C-ABI call) from "
                         f"pinned host memory; PCIe-bound", "timer": "host wall clock around the blocking C-ABI calls"}
 
