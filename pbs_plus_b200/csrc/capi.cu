@@ -551,6 +551,26 @@ static int job_enqueue(pbsgpu_job *j) {
     return job_enqueue_back(j);
 }
 
+// dense candidates (adversarial / highly structured data): replace the candidate buffers by exactly sized ones
+static int job_grow_cands(pbsgpu_job *j, unsigned long long nc) {
+    pbsgpu_ctx *ctx = j->ctx;
+    ctx->dev.put(j->d_cand); ctx->dev.put(j->d_cand_sorted); ctx->dev.put(j->d_temp);
+    j->d_cand = j->d_cand_sorted = nullptr; j->d_temp = nullptr;
+    j->cand_cap = nc + nc / 8 + 4096;
+    if (j->cand_cap >= (1ull << 31)) return fail(ctx, PBSGPU_ENOMEM, "candidate density too high (%llu candidates)", nc);
+    j->d_cand = (uint64_t *)ctx->dev.get(j->cand_cap * 8);
+    j->d_cand_sorted = (uint64_t *)ctx->dev.get(j->cand_cap * 8);
+    size_t t1 = 0, t2 = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, t1, (uint64_t *)nullptr, (uint64_t *)nullptr, (int)j->cand_cap);
+    if (j->want_digests)
+        cub::DeviceRadixSort::SortPairsDescending(nullptr, t2, (uint32_t *)nullptr, (uint32_t *)nullptr,
+                                                  (uint32_t *)nullptr, (uint32_t *)nullptr, (int)j->chunk_cap);
+    j->temp_bytes = std::max(t1, t2) + 256;
+    j->d_temp = ctx->dev.get(j->temp_bytes);
+    if (!j->d_cand || !j->d_cand_sorted || !j->d_temp) return fail(ctx, PBSGPU_ENOMEM, "device allocation failed (rerun)");
+    return PBSGPU_OK;
+}
+
 // Blocks until the job is done; reruns it with a larger candidate buffer if the
 // (statistically sized) one overflowed -- results are exact either way.
 static int job_finish(pbsgpu_job *j) {
@@ -559,21 +579,8 @@ static int job_finish(pbsgpu_job *j) {
         CK(cudaEventSynchronize(j->ev[EV_END]));
         unsigned long long nc = j->h_counters[0];
         if (nc <= j->cand_cap) break;
-        // dense candidates (adversarial / highly structured data): grow and redo
-        ctx->dev.put(j->d_cand); ctx->dev.put(j->d_cand_sorted); ctx->dev.put(j->d_temp);
-        j->d_cand = j->d_cand_sorted = nullptr; j->d_temp = nullptr;
-        j->cand_cap = nc + nc / 8 + 4096;
-        if (j->cand_cap >= (1ull << 31)) return fail(ctx, PBSGPU_ENOMEM, "candidate density too high (%llu candidates)", nc);
-        j->d_cand = (uint64_t *)ctx->dev.get(j->cand_cap * 8);
-        j->d_cand_sorted = (uint64_t *)ctx->dev.get(j->cand_cap * 8);
-        size_t t1 = 0, t2 = 0;
-        cub::DeviceRadixSort::SortKeys(nullptr, t1, (uint64_t *)nullptr, (uint64_t *)nullptr, (int)j->cand_cap);
-        if (j->want_digests)
-            cub::DeviceRadixSort::SortPairsDescending(nullptr, t2, (uint32_t *)nullptr, (uint32_t *)nullptr,
-                                                      (uint32_t *)nullptr, (uint32_t *)nullptr, (int)j->chunk_cap);
-        j->temp_bytes = std::max(t1, t2) + 256;
-        j->d_temp = ctx->dev.get(j->temp_bytes);
-        if (!j->d_cand || !j->d_cand_sorted || !j->d_temp) return fail(ctx, PBSGPU_ENOMEM, "device allocation failed (rerun)");
+        int grc = job_grow_cands(j, nc);
+        if (grc) return grc;
         j->reruns++;
         int rc = job_enqueue(j);
         if (rc) return rc;
@@ -1113,17 +1120,27 @@ extern "C" int pbsgpu_sha256_batch(pbsgpu_ctx *ctx, const void *base, const uint
 // ---------------------------------------------------------------------------
 // streaming form
 // ---------------------------------------------------------------------------
+// Windows are pipelined: when a window is full its scan + resolve run at once (the host needs the
+// cut points to know which tail is still undecided and must be carried into the next window), the carry
+// is copied to the next buffer, and the window's SHA-256 half is enqueued asynchronously -- so the serial
+// tail of a window's longest chunk overlaps the copies and scans of the following windows.  poll()
+// hands out the chunks of finished windows in stream order.
+constexpr int STREAM_NBUF = 6;   // windows in flight hide the ~0.3 s serial SHA tail of a window's longest chunk
+struct StreamJob { pbsgpu_job *j; int buf; uint64_t base_off; };
+
 struct pbsgpu_stream {
     pbsgpu_ctx *ctx;
     pbsgpu_cfg cfg;
     pbsgpu_set *set;
     uint64_t window;        // process when this many bytes are buffered
     uint64_t cap;           // device buffer capacity = window + max
-    uint8_t *buf[2];        // ping-pong (carry is copied to the other buffer)
+    uint8_t *buf[STREAM_NBUF];
+    bool busy[STREAM_NBUF]; // referenced by an in-flight window
     int cur;
     uint64_t fill;          // bytes buffered in buf[cur]
     uint64_t base_off;      // stream offset of buf[cur][0]
     bool finished, started;
+    std::vector<StreamJob> inflight;   // FIFO
     std::vector<pbsgpu_chunk> ready;
     size_t ready_pos;
 };
@@ -1134,13 +1151,41 @@ extern "C" int pbsgpu_stream_open(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg, pbsgpu
     if (!cfg_ok(cfg)) return fail(ctx, PBSGPU_EINVAL, "invalid pbsgpu_cfg (use pbsgpu_config)");
     pbsgpu_stream *s = new pbsgpu_stream();
     s->ctx = ctx; s->cfg = *cfg; s->set = set;
-    uint64_t w = 256ull << 20;
+    uint64_t w = 1ull << 30;   // bytes in flight (5 windows) / tail latency bounds the rate: ~15 GiB/s
     const char *e = getenv("PBSGPU_STREAM_WINDOW");
     if (e) w = strtoull(e, nullptr, 0);
     s->window = std::max<uint64_t>(w, (uint64_t)cfg->max);
-    s->cap = 0; s->buf[0] = s->buf[1] = nullptr; s->cur = 0; s->fill = 0; s->base_off = 0;
+    s->cap = 0; s->cur = 0; s->fill = 0; s->base_off = 0;
+    for (int i = 0; i < STREAM_NBUF; i++) { s->buf[i] = nullptr; s->busy[i] = false; }
     s->finished = false; s->started = false; s->ready_pos = 0;
     *out = s;
+    return PBSGPU_OK;
+}
+
+// collect finished windows (all of them if block) in order
+static int stream_collect(pbsgpu_stream *s, bool block) {
+    pbsgpu_ctx *ctx = s->ctx;
+    while (!s->inflight.empty()) {
+        StreamJob sj = s->inflight.front();
+        if (!block) {
+            cudaError_t q = cudaEventQuery(sj.j->ev[EV_END]);
+            if (q == cudaErrorNotReady) { (void)cudaGetLastError(); break; }
+        }
+        int rc = job_finish(sj.j);
+        if (rc != PBSGPU_OK) { cudaStreamSynchronize(sj.j->st); }
+        s->inflight.erase(s->inflight.begin());
+        s->busy[sj.buf] = false;
+        if (rc != PBSGPU_OK) { job_release(sj.j); return rc; }
+        const uint64_t nch = sj.j->h_counters[1];
+        const size_t before = s->ready.size();
+        for (uint64_t k = 0; k < nch; k++) {
+            pbsgpu_chunk c = sj.j->h_out[k];
+            c.stream = 0; c.end_off += sj.base_off;
+            s->ready.push_back(c);
+        }
+        job_release(sj.j);
+        if (s->set && nch) { rc = apply_set(s->set, s->ready.data() + before, nch); if (rc) return rc; }
+    }
     return PBSGPU_OK;
 }
 
@@ -1151,26 +1196,49 @@ static int stream_process(pbsgpu_stream *s, int eof) {
     pbsgpu_job *j = nullptr;
     int rc = job_create(ctx, &s->cfg, s->buf[s->cur], &off0, &len0, 1, eof, 1, &j);
     if (rc) return rc;
-    rc = job_enqueue(j);
-    if (rc == PBSGPU_OK) rc = job_finish(j);
-    if (rc != PBSGPU_OK) { cudaStreamSynchronize(j->st); job_release(j); return rc; }
-    uint64_t nch = j->h_counters[1];
-    uint64_t consumed = eof ? s->fill : j->h_consumed[0];
-    size_t before = s->ready.size();
-    for (uint64_t k = 0; k < nch; k++) {
-        pbsgpu_chunk c = j->h_out[k];
-        c.stream = 0; c.end_off += s->base_off;
-        s->ready.push_back(c);
+    // front half now: the cut points decide what has to be carried over
+    unsigned long long counters[4] = {0, 0, 0, 0};
+    uint64_t consumed = s->fill;
+    for (;;) {
+        rc = job_enqueue_front(j);
+        if (rc == PBSGPU_OK) {
+            cudaError_t e = cudaMemcpyAsync(counters, j->d_counters, sizeof counters, cudaMemcpyDeviceToHost, j->st);
+            if (e == cudaSuccess && !eof) e = cudaMemcpyAsync(&consumed, j->d_consumed, 8, cudaMemcpyDeviceToHost, j->st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(j->st);
+            if (e != cudaSuccess) { (void)cudaGetLastError(); rc = fail(ctx, PBSGPU_ECUDA, "stream window: %s", cudaGetErrorString(e)); }
+        }
+        if (rc != PBSGPU_OK) { cudaStreamSynchronize(j->st); job_release(j); return rc; }
+        if (counters[0] <= j->cand_cap) break;
+        rc = job_grow_cands(j, counters[0]);          // dense candidates: redo the front half with room for all
+        if (rc) { job_release(j); return rc; }
+        j->reruns++;
     }
-    job_release(j);
-    if (s->set && nch) { rc = apply_set(s->set, s->ready.data() + before, nch); if (rc) return rc; }
-    // carry the undecided tail to the other buffer
-    uint64_t rest = s->fill - consumed;
+    if (eof) consumed = s->fill;
+    const uint64_t rest = s->fill - consumed;
+    // next buffer (wait for the oldest window if all are referenced)
+    int next = -1;
+    for (;;) {
+        for (int i = 0; i < STREAM_NBUF; i++) if (i != s->cur && !s->busy[i]) { next = i; break; }
+        if (next >= 0 || s->inflight.empty()) break;
+        StreamJob oldest = s->inflight.front();
+        cudaEventSynchronize(oldest.j->ev[EV_END]);
+        rc = stream_collect(s, false);
+        if (rc) { cudaStreamSynchronize(j->st); job_release(j); return rc; }
+    }
+    if (next < 0) { cudaStreamSynchronize(j->st); job_release(j); return fail(ctx, PBSGPU_ESTATE, "internal: no free stream buffer"); }
+    if (!s->buf[next]) {
+        s->buf[next] = (uint8_t *)ctx->dev.get(s->cap);
+        if (!s->buf[next]) { cudaStreamSynchronize(j->st); job_release(j); return fail(ctx, PBSGPU_ENOMEM, "stream buffer of %llu bytes failed", (unsigned long long)s->cap); }
+    }
     if (rest) {
-        CK(cudaMemcpyAsync(s->buf[s->cur ^ 1], s->buf[s->cur] + consumed, rest, cudaMemcpyDeviceToDevice, ctx->streams[0]));
-        CK(cudaStreamSynchronize(ctx->streams[0]));
+        CK(cudaMemcpyAsync(s->buf[next], s->buf[s->cur] + consumed, rest, cudaMemcpyDeviceToDevice, ctx->copy_stream));
+        CK(cudaStreamSynchronize(ctx->copy_stream));
     }
-    s->cur ^= 1; s->fill = rest; s->base_off += consumed;
+    rc = job_enqueue_back(j);                          // SHA-256 etc. run while the next window fills
+    if (rc != PBSGPU_OK) { cudaStreamSynchronize(j->st); job_release(j); return rc; }
+    s->busy[s->cur] = true;
+    s->inflight.push_back(StreamJob{j, s->cur, s->base_off});
+    s->cur = next; s->fill = rest; s->base_off += consumed;
     return PBSGPU_OK;
 }
 
@@ -1181,23 +1249,23 @@ extern "C" int pbsgpu_stream_write(pbsgpu_stream *s, const void *data, uint64_t 
     if (s->finished) return fail(ctx, PBSGPU_ESTATE, "stream already finished");
     if (!s->started) {
         s->cap = s->window + s->cfg.max + 256;
-        s->buf[0] = (uint8_t *)ctx->dev.get(s->cap); s->buf[1] = (uint8_t *)ctx->dev.get(s->cap);
-        if (!s->buf[0] || !s->buf[1]) return fail(ctx, PBSGPU_ENOMEM, "stream buffers of %llu bytes failed", (unsigned long long)s->cap);
+        s->buf[0] = (uint8_t *)ctx->dev.get(s->cap);      // further buffers are allocated when first needed
+        if (!s->buf[0]) return fail(ctx, PBSGPU_ENOMEM, "stream buffer of %llu bytes failed", (unsigned long long)s->cap);
         s->started = true;
     }
     const uint8_t *p = (const uint8_t *)data;
     while (len) {
         uint64_t room = s->cap - s->fill;
         uint64_t take = std::min(len, std::min(room, s->window > s->fill ? s->window - s->fill : 0));
-        if (take == 0) {   // window full: process, keeping the undecided tail
+        if (take == 0) {   // window full: cut what can be cut, keep the undecided tail
             int rc = stream_process(s, 0);
             if (rc) return rc;
             if (s->fill >= s->window) return fail(ctx, PBSGPU_ESTATE, "internal: stream window did not drain");
             continue;
         }
-        // ordered on one of our (non-blocking) streams and completed before any kernel may read it
-        CK(cudaMemcpyAsync(s->buf[s->cur] + s->fill, p, take, cudaMemcpyHostToDevice, ctx->streams[0]));
-        CK(cudaStreamSynchronize(ctx->streams[0]));
+        // ordered on the copy stream and completed before any kernel may read it
+        CK(cudaMemcpyAsync(s->buf[s->cur] + s->fill, p, take, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CK(cudaStreamSynchronize(ctx->copy_stream));
         s->fill += take; p += take; len -= take;
     }
     if (s->fill >= s->window) return stream_process(s, 0);
@@ -1209,6 +1277,7 @@ extern "C" int pbsgpu_stream_finish(pbsgpu_stream *s) {
     Guard g(s->ctx);
     if (s->finished) return PBSGPU_OK;
     int rc = stream_process(s, 1);
+    if (rc == PBSGPU_OK) rc = stream_collect(s, true);
     if (rc == PBSGPU_OK) s->finished = true;
     return rc;
 }
@@ -1216,6 +1285,8 @@ extern "C" int pbsgpu_stream_finish(pbsgpu_stream *s) {
 extern "C" int pbsgpu_stream_poll(pbsgpu_stream *s, pbsgpu_chunk *out, uint64_t cap, uint64_t *n_out) {
     if (!s || !n_out || (cap && !out)) return PBSGPU_EINVAL;
     Guard g(s->ctx);
+    int rc = stream_collect(s, false);
+    if (rc) return rc;
     uint64_t avail = s->ready.size() - s->ready_pos;
     uint64_t k = std::min(avail, cap);
     if (k) memcpy(out, s->ready.data() + s->ready_pos, k * sizeof(pbsgpu_chunk));
@@ -1228,7 +1299,8 @@ extern "C" int pbsgpu_stream_poll(pbsgpu_stream *s, pbsgpu_chunk *out, uint64_t 
 extern "C" void pbsgpu_stream_close(pbsgpu_stream *s) {
     if (!s) return;
     Guard g(s->ctx);
-    s->ctx->dev.put(s->buf[0]); s->ctx->dev.put(s->buf[1]);
+    for (auto &sj : s->inflight) { cudaEventSynchronize(sj.j->ev[EV_END]); cudaStreamSynchronize(sj.j->st); job_release(sj.j); }
+    for (int i = 0; i < STREAM_NBUF; i++) s->ctx->dev.put(s->buf[i]);
     delete s;
 }
 
