@@ -106,6 +106,10 @@ type Chunk struct {
 	Digest [32]byte
 }
 
+// ErrStagingFull is returned by WriteEntryReader when the pinned staging buffer cannot take the entry:
+// Flush the batch and write the entry again.
+var ErrStagingFull = errors.New("pbsgpu: staging full, call Flush first")
+
 // Batch accumulates whole files in C-owned PINNED staging (Go pointers are never retained by C)
 // and pushes them through the GPU in one call -- the batched form of the per-file loop at
 // commit.go:604-625 / :697-731.
@@ -132,7 +136,7 @@ func (e *Engine) NewBatch(cfg Config, stagingBytes uint64) (*Batch, error) {
 func (b *Batch) WriteEntryReader(r io.Reader, size uint64) error {
 	start := (b.fill + 255) &^ 255
 	if start+size > b.cap {
-		return errors.New("pbsgpu: staging full, call Flush first")
+		return ErrStagingFull
 	}
 	dst := unsafe.Slice((*byte)(unsafe.Add(b.buf, start)), size)
 	if _, err := io.ReadFull(r, dst); err != nil {
