@@ -531,3 +531,31 @@ def test_mostly_long_chunks_are_capped_for_the_latency_partition(eng, torch):
     rec = eng.chunk_digest_batch(pg.make_config(4096), to_dev(torch, data), [0], [n])     # 6144 chunks of 16 KiB
     assert len(rec) > 24 * 32 * 4
     assert rec.tobytes() == oracle.chunk_digest(oracle.config(4096), data).tobytes()
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_structured_data_kinds_match_oracle(eng, torch, variant):
+    """Zeros, low-entropy, periodic and text-like data (where candidates are absent or dense and cuts are
+    forced) through scan + SHA-256, both kernel variants."""
+    eng.set_kernel_variant(variant)
+    try:
+        rng = np.random.default_rng(91)
+        kinds = {
+            "zeros": np.zeros(700_000, dtype=np.uint8),
+            "ff": np.full(300_001, 255, dtype=np.uint8),
+            "two-symbols": rng.integers(0, 2, size=500_000, dtype=np.uint8),
+            "three-symbols": rng.integers(0, 3, size=500_003, dtype=np.uint8),
+            "period-7": np.resize(rng.integers(0, 256, size=7, dtype=np.uint8), 400_000),
+            "period-64": np.resize(rng.integers(0, 256, size=64, dtype=np.uint8), 400_000),
+            "period-1000": np.resize(rng.integers(0, 256, size=1000, dtype=np.uint8), 600_000),
+            "text": np.frombuffer((b"the quick brown fox jumps over the lazy dog\n" * 20000)[:777_777], dtype=np.uint8).copy(),
+            "ramp": (np.arange(650_000) % 251).astype(np.uint8),
+        }
+        arrs = list(kinds.values())
+        buf, off, ln = pack(arrs, align=16, lead=16)
+        for avg in (256, 4096, 65536):
+            rec = eng.chunk_digest_batch(pg.make_config(avg), to_dev(torch, buf), off, ln)
+            ref = oracle.chunk_digest_streams(oracle.config(avg), arrs, threads=4)
+            assert rec.tobytes() == ref.tobytes(), (avg, variant)
+    finally:
+        eng.set_kernel_variant(0)
