@@ -151,9 +151,21 @@ func (b *Batch) WriteEntryReader(r io.Reader, size uint64) error {
 // Flush runs scan -> cut -> SHA-256 -> probe for every queued file and returns the chunks in
 // (file, offset) order; Known chunks need no upload ("Only new chunks are uploaded").
 func (b *Batch) Flush(known *KnownSet) ([]Chunk, error) {
+	res, _, err := b.flush(known, false)
+	return res, err
+}
+
+// FlushWithHashes is Flush plus the XXH3-64 (seed 0) of every queued file, computed on the GPU from the
+// same staged bytes: the value emitBackedFile gets from `h := xxh3.New(); io.TeeReader(f, h); h.Sum64()`
+// (commit.go:717-725) and stores in ow.backedHashes -- so the host no longer hashes while it reads.
+func (b *Batch) FlushWithHashes(known *KnownSet) ([]Chunk, []uint64, error) {
+	return b.flush(known, true)
+}
+
+func (b *Batch) flush(known *KnownSet, withHashes bool) ([]Chunk, []uint64, error) {
 	n := len(b.off)
 	if n == 0 {
-		return nil, nil
+		return nil, nil, nil
 	}
 	capChunks := uint64(n)
 	for _, l := range b.ln {
@@ -165,10 +177,16 @@ func (b *Batch) Flush(known *KnownSet) ([]Chunk, error) {
 	if known != nil {
 		set = known.s
 	}
-	rc := C.pbsgpu_chunk_digest_batch(b.e.ctx, &b.cfg.c, b.buf, &b.off[0], &b.ln[0], C.uint32_t(n), set,
-		&out[0], C.uint64_t(len(out)), &nOut)
+	var hashes []C.uint64_t
+	var hp *C.uint64_t
+	if withHashes {
+		hashes = make([]C.uint64_t, n)
+		hp = &hashes[0]
+	}
+	rc := C.pbsgpu_chunk_digest_batch_xxh3(b.e.ctx, &b.cfg.c, b.buf, &b.off[0], &b.ln[0], C.uint32_t(n), set,
+		&out[0], C.uint64_t(len(out)), &nOut, hp)
 	if err := b.e.err(rc); err != nil {
-		return nil, err
+		return nil, nil, err
 	}
 	res := make([]Chunk, int(nOut))
 	for i := range res {
@@ -177,8 +195,15 @@ func (b *Batch) Flush(known *KnownSet) ([]Chunk, error) {
 		res[i].End = uint64(out[i].end_off)
 		copy(res[i].Digest[:], C.GoBytes(unsafe.Pointer(&out[i].digest[0]), 32))
 	}
+	var hs []uint64
+	if withHashes {
+		hs = make([]uint64, n)
+		for i := range hashes {
+			hs[i] = uint64(hashes[i])
+		}
+	}
 	b.off, b.ln, b.fill = b.off[:0], b.ln[:0], 0
-	return res, nil
+	return res, hs, nil
 }
 
 func (b *Batch) Close() { C.pbsgpu_host_free(b.e.ctx, b.buf) }

@@ -196,6 +196,21 @@ int pbsgpu_crc32_batch(pbsgpu_ctx *ctx, const void *base, const uint64_t *off, c
                        uint32_t *crc_out);
 void pbsgpu_blob_header(uint32_t crc, uint8_t out[12]);
 
+/* ---- f2 ("next" row): the commit walk's per-file content hash ----------------------------------
+ * emitBackedFile tees every new file through `xxh3.New()` and keeps `h.Sum64()` (reference
+ * internal/pxarmount/commit.go:717-725); verifyBackedFileHashes later re-reads every file to recompute
+ * it (commit.go:957-976).  XXH3-64, seed 0, default secret (github.com/zeebo/xxh3, go.mod; the published
+ * xxHash v0.8 algorithm -- tests pin it against libxxhash).
+ * pbsgpu_xxh3_batch hashes n byte ranges (HOST or DEVICE base) on the GPU.
+ * pbsgpu_chunk_digest_batch_xxh3 is pbsgpu_chunk_digest_batch plus stream_xxh3[n] (may be NULL): the
+ * XXH3-64 of every stream computed from the SAME staged bytes the chunker and SHA-256 read, so the
+ * batched commit walk needs no second pass over the file on the host. */
+int pbsgpu_xxh3_batch(pbsgpu_ctx *ctx, const void *base, const uint64_t *off, const uint64_t *len, uint32_t n,
+                      uint64_t *hash_out);
+int pbsgpu_chunk_digest_batch_xxh3(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg, const void *base, const uint64_t *off,
+                                   const uint64_t *len, uint32_t n, pbsgpu_set *set, pbsgpu_chunk *out, uint64_t cap,
+                                   uint64_t *n_out, uint64_t *stream_xxh3);
+
 /* ---- pinned staging owned by C, filled by the Go side ----------------------------- */
 void *pbsgpu_host_alloc(pbsgpu_ctx *ctx, uint64_t bytes);
 void pbsgpu_host_free(pbsgpu_ctx *ctx, void *p);

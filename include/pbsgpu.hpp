@@ -12,6 +12,7 @@
 #include <cstdint>
 #include <cstring>
 #include <functional>
+#include <map>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -105,9 +106,11 @@ class DedupWriter {
         uint64_t cap = entries_.size();
         for (uint64_t l : len_) cap += l / (cfg_.min > 64 ? cfg_.min : 65);
         std::vector<pbsgpu_chunk> out(cap + 1);
+        std::vector<uint64_t> xxh(entries_.size());
         uint64_t n = 0;
-        e_.check(pbsgpu_chunk_digest_batch(e_.ctx(), &cfg_, buf_, off_.data(), len_.data(), (uint32_t)entries_.size(),
-                                           known_ ? known_->handle() : nullptr, out.data(), out.size(), &n));
+        e_.check(pbsgpu_chunk_digest_batch_xxh3(e_.ctx(), &cfg_, buf_, off_.data(), len_.data(), (uint32_t)entries_.size(),
+                                                known_ ? known_->handle() : nullptr, out.data(), out.size(), &n, xxh.data()));
+        for (size_t i = 0; i < entries_.size(); i++) backed_hashes_[entries_[i].Path] = xxh[i];
         for (uint64_t i = 0; i < n; i++) {
             IndexRecord r;
             r.path = entries_[out[i].stream].Path; r.end_off = out[i].end_off;
@@ -117,6 +120,8 @@ class DedupWriter {
         entries_.clear(); off_.clear(); len_.clear(); fill_ = 0;
     }
     const std::vector<IndexRecord> &Finish() { Flush(); finished_ = true; return index_; }
+    // relPath -> XXH3-64 of the uploaded bytes: commitWalkState.backedHashes (commit.go:187, :725)
+    const std::map<std::string, uint64_t> &BackedHashes() const { return backed_hashes_; }
 
   private:
     Engine &e_;
@@ -128,6 +133,7 @@ class DedupWriter {
     std::vector<Entry> entries_;
     std::vector<uint64_t> off_, len_;
     std::vector<IndexRecord> index_;
+    std::map<std::string, uint64_t> backed_hashes_;
 };
 
 }  // namespace transfer

@@ -95,6 +95,8 @@ def lib():
         L.orc_corpus_fill.argtypes = [C.POINTER(Corpus), C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64]
         L.orc_chunk_digest_mt.argtypes = [C.POINTER(Cfg), C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
                                           C.c_void_p, C.c_uint64, C.c_void_p]
+        L.orc_xxh3_64.argtypes = [C.c_void_p, C.c_uint64]
+        L.orc_xxh3_64.restype = C.c_uint64
         L.orc_corpus_fill_mt.argtypes = [C.POINTER(Corpus), C.c_uint64, C.c_void_p, C.c_uint32, C.c_uint32]
         _lib = L
     return _lib
@@ -154,6 +156,12 @@ def sha256(data) -> bytes:
     out = np.empty(32, dtype=np.uint8)
     lib().orc_sha256(a.ctypes.data if len(a) else None, len(a), out.ctypes.data)
     return out.tobytes()
+
+
+def xxh3_64(data) -> int:
+    """XXH3-64, seed 0 (what xxh3.New()...Sum64() returns at commit.go:717-725)."""
+    b = _buf(data)
+    return int(lib().orc_xxh3_64(b.ctypes.data, b.size))
 
 
 def force_portable_sha(on: bool) -> None:

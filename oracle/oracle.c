@@ -543,3 +543,100 @@ int orc_corpus_fill_mt(const orc_corpus *c, uint64_t first_file, uint8_t *const 
     for (uint32_t t = 0; t < threads; t++) pthread_join(th[t], NULL);
     return 0;
 }
+
+/* ====================================================================================================
+ * XXH3-64 (seed 0, default secret) -- SURVEY.md section 8 row f2: the per-file content hash the commit
+ * walk computes through xxh3.New()/Sum64() (reference internal/pxarmount/commit.go:717-725) and
+ * re-computes in verifyBackedFileHashes (commit.go:957-976).  The Go module github.com/zeebo/xxh3
+ * (go.mod) implements the published XXH3 algorithm (xxHash v0.8 specification); this is a scalar
+ * restatement of that specification.  PINNED: tests/test_oracle.py checks it against the independent
+ * python-xxhash binding (libxxhash) for every length 0..2100 and random long inputs.
+ * ==================================================================================================== */
+static const uint8_t XXH3_SECRET[192] = {
+    0xb8, 0xfe, 0x6c, 0x39, 0x23, 0xa4, 0x4b, 0xbe, 0x7c, 0x01, 0x81, 0x2c, 0xf7, 0x21, 0xad, 0x1c,
+    0xde, 0xd4, 0x6d, 0xe9, 0x83, 0x90, 0x97, 0xdb, 0x72, 0x40, 0xa4, 0xa4, 0xb7, 0xb3, 0x67, 0x1f,
+    0xcb, 0x79, 0xe6, 0x4e, 0xcc, 0xc0, 0xe5, 0x78, 0x82, 0x5a, 0xd0, 0x7d, 0xcc, 0xff, 0x72, 0x21,
+    0xb8, 0x08, 0x46, 0x74, 0xf7, 0x43, 0x24, 0x8e, 0xe0, 0x35, 0x90, 0xe6, 0x81, 0x3a, 0x26, 0x4c,
+    0x3c, 0x28, 0x52, 0xbb, 0x91, 0xc3, 0x00, 0xcb, 0x88, 0xd0, 0x65, 0x8b, 0x1b, 0x53, 0x2e, 0xa3,
+    0x71, 0x64, 0x48, 0x97, 0xa2, 0x0d, 0xf9, 0x4e, 0x38, 0x19, 0xef, 0x46, 0xa9, 0xde, 0xac, 0xd8,
+    0xa8, 0xfa, 0x76, 0x3f, 0xe3, 0x9c, 0x34, 0x3f, 0xf9, 0xdc, 0xbb, 0xc7, 0xc7, 0x0b, 0x4f, 0x1d,
+    0x8a, 0x51, 0xe0, 0x4b, 0xcd, 0xb4, 0x59, 0x31, 0xc8, 0x9f, 0x7e, 0xc9, 0xd9, 0x78, 0x73, 0x64,
+    0xea, 0xc5, 0xac, 0x83, 0x34, 0xd3, 0xeb, 0xc3, 0xc5, 0x81, 0xa0, 0xff, 0xfa, 0x13, 0x63, 0xeb,
+    0x17, 0x0d, 0xdd, 0x51, 0xb7, 0xf0, 0xda, 0x49, 0xd3, 0x16, 0x55, 0x26, 0x29, 0xd4, 0x68, 0x9e,
+    0x2b, 0x16, 0xbe, 0x58, 0x7d, 0x47, 0xa1, 0xfc, 0x8f, 0xf8, 0xb8, 0xd1, 0x7a, 0xd0, 0x31, 0xce,
+    0x45, 0xcb, 0x3a, 0x8f, 0x95, 0x16, 0x04, 0x28, 0xaf, 0xd7, 0xfb, 0xca, 0xbb, 0x4b, 0x40, 0x7e,
+};
+const uint8_t *orc_xxh3_secret(void) { return XXH3_SECRET; }
+
+#define XP32_1 0x9E3779B1u
+#define XP32_2 0x85EBCA77u
+#define XP32_3 0xC2B2AE3Du
+#define XP64_1 0x9E3779B185EBCA87ull
+#define XP64_2 0xC2B2AE3D27D4EB4Full
+#define XP64_3 0x165667B19E3779F9ull
+#define XP64_4 0x85EBCA77C2B2AE63ull
+#define XP64_5 0x27D4EB2F165667C5ull
+#define XPMX1 0x165667919E3779F9ull
+#define XPMX2 0x9FB21C651E98DF25ull
+
+static inline uint64_t x_le64(const uint8_t *p) { uint64_t v; memcpy(&v, p, 8); return v; }   /* little-endian host */
+static inline uint32_t x_le32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v; }
+static inline uint64_t x_rotl64(uint64_t x, unsigned r) { return (x << r) | (x >> (64 - r)); }
+static inline uint64_t x_fold(uint64_t a, uint64_t b) { __uint128_t m = (__uint128_t)a * b; return (uint64_t)m ^ (uint64_t)(m >> 64); }
+static inline uint64_t x_aval3(uint64_t h) { h ^= h >> 37; h *= XPMX1; h ^= h >> 32; return h; }
+static inline uint64_t x_aval64(uint64_t h) { h ^= h >> 33; h *= XP64_2; h ^= h >> 29; h *= XP64_3; h ^= h >> 32; return h; }
+static inline uint64_t x_mix16(const uint8_t *in, const uint8_t *sec) { return x_fold(x_le64(in) ^ x_le64(sec), x_le64(in + 8) ^ x_le64(sec + 8)); }
+static inline void x_acc512(uint64_t acc[8], const uint8_t *in, const uint8_t *sec) {
+    for (int i = 0; i < 8; i++) {
+        uint64_t dv = x_le64(in + 8 * i), dk = dv ^ x_le64(sec + 8 * i);
+        acc[i ^ 1] += dv;
+        acc[i] += (uint64_t)(uint32_t)dk * (dk >> 32);
+    }
+}
+
+uint64_t orc_xxh3_64(const uint8_t *in, uint64_t len) {
+    const uint8_t *S = XXH3_SECRET;
+    if (len == 0) return x_aval64(x_le64(S + 56) ^ x_le64(S + 64));
+    if (len <= 3) {
+        uint32_t comb = ((uint32_t)in[0] << 16) | ((uint32_t)in[len >> 1] << 24) | in[len - 1] | ((uint32_t)len << 8);
+        return x_aval64((uint64_t)comb ^ (uint64_t)(x_le32(S) ^ x_le32(S + 4)));
+    }
+    if (len <= 8) {
+        uint64_t flip = x_le64(S + 8) ^ x_le64(S + 16);
+        uint64_t h = ((uint64_t)x_le32(in + len - 4) + ((uint64_t)x_le32(in) << 32)) ^ flip;
+        h ^= x_rotl64(h, 49) ^ x_rotl64(h, 24); h *= XPMX2; h ^= (h >> 35) + len; h *= XPMX2;
+        return h ^ (h >> 28);
+    }
+    if (len <= 16) {
+        uint64_t lo = x_le64(in) ^ (x_le64(S + 24) ^ x_le64(S + 32)), hi = x_le64(in + len - 8) ^ (x_le64(S + 40) ^ x_le64(S + 48));
+        return x_aval3(len + __builtin_bswap64(lo) + hi + x_fold(lo, hi));
+    }
+    if (len <= 128) {
+        uint64_t acc = len * XP64_1;
+        for (int i = (int)((len - 1) / 32); i >= 0; i--) {
+            acc += x_mix16(in + 16 * i, S + 32 * i);
+            acc += x_mix16(in + len - 16 * (i + 1), S + 32 * i + 16);
+        }
+        return x_aval3(acc);
+    }
+    if (len <= 240) {
+        uint64_t acc = len * XP64_1;
+        for (int i = 0; i < 8; i++) acc += x_mix16(in + 16 * i, S + 16 * i);
+        uint64_t end = x_mix16(in + len - 16, S + 136 - 17);
+        acc = x_aval3(acc);
+        for (unsigned i = 8; i < len / 16; i++) end += x_mix16(in + 16 * i, S + 16 * (i - 8) + 3);
+        return x_aval3(acc + end);
+    }
+    uint64_t acc[8] = {XP32_3, XP64_1, XP64_2, XP64_3, XP64_4, XP32_2, XP64_5, XP32_1};
+    const uint64_t nb = (len - 1) / 1024;
+    for (uint64_t n = 0; n < nb; n++) {
+        for (int s = 0; s < 16; s++) x_acc512(acc, in + n * 1024 + 64 * s, S + 8 * s);
+        for (int i = 0; i < 8; i++) acc[i] = (acc[i] ^ (acc[i] >> 47) ^ x_le64(S + 128 + 8 * i)) * XP32_1;
+    }
+    const uint64_t ns = ((len - 1) - 1024 * nb) / 64;
+    for (uint64_t s = 0; s < ns; s++) x_acc512(acc, in + nb * 1024 + 64 * s, S + 8 * s);
+    x_acc512(acc, in + len - 64, S + 192 - 64 - 7);
+    uint64_t r = len * XP64_1;
+    for (int i = 0; i < 4; i++) r += x_fold(acc[2 * i] ^ x_le64(S + 11 + 16 * i), acc[2 * i + 1] ^ x_le64(S + 11 + 16 * i + 8));
+    return x_aval3(r);
+}

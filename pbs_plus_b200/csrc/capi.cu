@@ -89,6 +89,7 @@ struct pbsgpu_ctx {
     // device copies of the chunker table (re-uploaded when the cfg table changes)
     uint32_t *d_table = nullptr, *d_rot = nullptr;
     void *d_crc_tables = nullptr;   // K6 tables, uploaded on first use
+    void *d_xxh_tab = nullptr;      // K7 secret words, uploaded on first use
     uint32_t table_cache[256];
     bool table_valid = false;
     pbsgpu_timing last_timing;
@@ -99,6 +100,8 @@ struct pbsgpu_ctx {
     int part_sms = 0, bulk_sms = 0;
     CUgreenCtx g_long = nullptr, g_bulk = nullptr;
     uint64_t stage_bytes = 0;   // host-input staging size (0 = auto)
+    bool scan_lanes = false;
+    uint64_t xxh3_cap_blocks = 8ull << 20;   // 8 GiB of input, 512 MiB of block sums per pass
 };
 
 static int fail(pbsgpu_ctx *c, int code, const char *fmt, ...) {
@@ -226,6 +229,10 @@ extern "C" int pbsgpu_open(int device, pbsgpu_ctx **out) {
     if (sb) ctx->stage_bytes = strtoull(sb, nullptr, 0);
     const char *v = getenv("PBSGPU_VARIANT");
     if (v) ctx->variant = atoi(v);
+    const char *sl = getenv("PBSGPU_SCAN_LANES");      // 1 = lane-contiguous scan kernel (k_scan_lanes), default off
+    if (sl) ctx->scan_lanes = atoi(sl) != 0;
+    const char *xc = getenv("PBSGPU_XXH3_CAP_BLOCKS");  // per-pass block budget of K7 (tests force several passes)
+    if (xc && atoll(xc) > 0) ctx->xxh3_cap_blocks = (uint64_t)atoll(xc);
     *out = ctx;
     return PBSGPU_OK;
 }
@@ -238,6 +245,7 @@ extern "C" void pbsgpu_close(pbsgpu_ctx *ctx) {
     cudaStreamDestroy(ctx->copy_stream);
     cudaFree(ctx->d_table); cudaFree(ctx->d_rot);
     if (ctx->d_crc_tables) cudaFree(ctx->d_crc_tables);
+    if (ctx->d_xxh_tab) cudaFree(ctx->d_xxh_tab);
     if (ctx->epoch) cudaEventDestroy(ctx->epoch);
     if (ctx->g_long || ctx->g_bulk) {
         auto gdestroy = driver_ep<CUresult (*)(CUgreenCtx)>("cuGreenCtxDestroy");
@@ -308,6 +316,7 @@ struct pbsgpu_job {
     uint32_t n = 0;
     uint64_t total_bytes = 0, total_tiles = 0, chunk_cap = 0, cand_cap = 0;
     int eof = 1, want_digests = 1, variant = 0;
+    bool scan_lanes = false;
     // device
     uint64_t *d_off = nullptr, *d_len = nullptr, *d_tile_first = nullptr, *d_cand = nullptr, *d_cand_sorted = nullptr;
     unsigned long long *d_counters = nullptr;   // [0] cand_count [1] n_chunks
@@ -399,13 +408,20 @@ static int job_create(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg, const void *base_d
     j->want_digests = want_digests; j->variant = ctx->variant; j->profiling = ctx->profiling;
     j->off.assign(off, off + n); j->len.assign(len, len + n);
     const uint64_t tile = j->variant == 1 ? (uint64_t)SIMPLE_SPAN : (uint64_t)WARP_TILE;
+    j->scan_lanes = j->variant == 0 && ctx->scan_lanes;
+    const uint64_t super = scan_lanes_super_bytes(), super_steps = scan_lanes_steps();
     j->tile_first.resize(n + 1);
     uint64_t tiles = 0, total = 0, chunks = 0;
     const uint64_t min_eff = min_effective(cfg->min);
     for (uint32_t i = 0; i < n; i++) {
         if (len[i] >= (1ull << KEY_POS_BITS)) { delete j; return fail(ctx, PBSGPU_EINVAL, "stream %u longer than 2^40 bytes", i); }
         j->tile_first[i] = tiles;
-        tiles += (len[i] + tile - 1) / tile;
+        if (j->scan_lanes) {   // k_scan_lanes: 8 steps per 64 KiB super-tile of a 16 B aligned stream, then plain tiles
+            const uint64_t ns = (((uintptr_t)(j->base + off[i])) & 15) == 0 ? len[i] / super : 0;
+            tiles += ns * super_steps + (len[i] - ns * super + tile - 1) / tile;
+        } else {
+            tiles += (len[i] + tile - 1) / tile;
+        }
         total += len[i];
         chunks += len[i] / min_eff + 1;
     }
@@ -460,6 +476,7 @@ static int job_enqueue_front(pbsgpu_job *j) {
     sa.total_tiles = j->total_tiles; sa.mask = j->cfg.mask; sa.break_min = j->cfg.break_min; sa.table = ctx->d_table;
     sa.cand = j->d_cand; sa.cand_cap = j->cand_cap; sa.cand_count = &j->d_counters[0];
     if (j->variant == 1) CK(launch_scan_simple(sa, st));
+    else if (j->scan_lanes) CK(launch_scan_lanes(sa, ctx->d_rot, ctx->sm_count, st));
     else CK(launch_scan_tuned(sa, ctx->d_rot, ctx->sm_count, st));
     CK(cudaEventRecord(j->ev[EV_SCAN], st));   // also the "scan done" signal a predecessor's back half waits for
     // candidates -> sorted by (stream, position)
@@ -911,6 +928,110 @@ extern "C" int pbsgpu_crc32_batch(pbsgpu_ctx *ctx, const void *base, const uint6
     return rc;
 }
 
+// ---------------------------------------------------------------------------
+// f2: XXH3-64 of n byte ranges (the commit walk's per-file content hash, commit.go:717-725, :957-976).
+// Blocks are hashed in passes of at most PBSGPU_XXH3_CAP_BLOCKS (default 8 Mi = 8 GiB of input, 512 MiB
+// of per-block sums); a pass takes the same block window of EVERY stream so the chains stay parallel.
+// xxh3_enqueue only enqueues (all passes, no host wait) so the fused batch call can put it on a job's
+// stream; xxh3_collect waits for the stream and brings the n hashes back.
+// ---------------------------------------------------------------------------
+struct XxhRun {
+    uint64_t *d_off = nullptr, *d_len = nullptr, *d_first = nullptr, *d_out = nullptr, *d_state = nullptr, *d_S = nullptr;
+    uint32_t n = 0;
+};
+
+static void xxh3_release(pbsgpu_ctx *ctx, XxhRun *r) {
+    ctx->dev.put(r->d_off); ctx->dev.put(r->d_len); ctx->dev.put(r->d_first); ctx->dev.put(r->d_out);
+    ctx->dev.put(r->d_state); ctx->dev.put(r->d_S);
+    *r = XxhRun();
+}
+
+static int xxh3_enqueue(pbsgpu_ctx *ctx, const uint8_t *dbase, const uint64_t *off, const uint64_t *len, uint32_t n,
+                        cudaStream_t st, XxhRun *r) {
+    if (!ctx->d_xxh_tab) {
+        std::vector<uint8_t> h(xxh3_tables_bytes());
+        xxh3_fill_tables_host(h.data());
+        CK(cudaMalloc(&ctx->d_xxh_tab, h.size()));
+        CK(cudaMemcpy(ctx->d_xxh_tab, h.data(), h.size(), cudaMemcpyHostToDevice));
+    }
+    const uint64_t cap_blocks = ctx->xxh3_cap_blocks;
+    uint64_t total_all = 0, max_nb = 0, n_long = 0;
+    std::vector<uint64_t> nb(n);
+    for (uint32_t i = 0; i < n; i++) {
+        nb[i] = len[i] > 240 ? (len[i] - 1) >> 10 : 0;
+        total_all += nb[i]; max_nb = std::max(max_nb, nb[i]); n_long += nb[i] != 0;
+    }
+    const bool one = total_all <= cap_blocks;
+    const uint64_t win = one ? std::max<uint64_t>(max_nb, 1) : std::max<uint64_t>(1, cap_blocks / n_long);
+    const uint64_t s_blocks = one ? total_all : std::min(total_all, n_long * win);
+    const uint64_t passes = (max_nb + win - 1) / win;
+    r->n = n;
+    r->d_off = (uint64_t *)ctx->dev.get(n * 8); r->d_len = (uint64_t *)ctx->dev.get(n * 8);
+    r->d_first = (uint64_t *)ctx->dev.get(std::max<uint64_t>(passes, 1) * (n + 1) * 8);
+    r->d_out = (uint64_t *)ctx->dev.get((uint64_t)n * 8); r->d_state = (uint64_t *)ctx->dev.get((uint64_t)n * 64);
+    r->d_S = (uint64_t *)ctx->dev.get(std::max<uint64_t>(s_blocks, 1) * 64);
+    if (!r->d_off || !r->d_len || !r->d_first || !r->d_out || !r->d_state || !r->d_S) {
+        xxh3_release(ctx, r);
+        return fail(ctx, PBSGPU_ENOMEM, "xxh3: device allocation failed");
+    }
+    cudaError_t e = cudaMemcpyAsync(r->d_off, off, n * 8, cudaMemcpyHostToDevice, st);   // pageable sources are staged before return
+    if (e == cudaSuccess) e = cudaMemcpyAsync(r->d_len, len, n * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = launch_xxh3_small(dbase, r->d_off, r->d_len, n, ctx->d_xxh_tab, r->d_out, st);
+    std::vector<uint64_t> first(n + 1);
+    uint64_t pass = 0;
+    for (uint64_t lo = 0; e == cudaSuccess && lo < max_nb; lo += win, pass++) {
+        uint64_t total = 0;
+        for (uint32_t i = 0; i < n; i++) {
+            first[i] = total;
+            if (nb[i] > lo) total += std::min(nb[i] - lo, win);
+        }
+        first[n] = total;
+        uint64_t *df = r->d_first + pass * (n + 1);
+        e = cudaMemcpyAsync(df, first.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = launch_xxh3_pass(dbase, r->d_off, r->d_len, df, n, total, lo, win, ctx->d_xxh_tab, r->d_S, r->d_state, r->d_out, st);
+    }
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        cudaStreamSynchronize(st);
+        xxh3_release(ctx, r);
+        return fail(ctx, PBSGPU_ECUDA, "xxh3: %s", cudaGetErrorString(e));
+    }
+    return PBSGPU_OK;
+}
+
+static int xxh3_collect(pbsgpu_ctx *ctx, XxhRun *r, uint64_t *hash_out, cudaStream_t st) {
+    if (!r->d_out) return PBSGPU_OK;
+    cudaError_t e = cudaMemcpyAsync(hash_out, r->d_out, (uint64_t)r->n * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    xxh3_release(ctx, r);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(ctx, PBSGPU_ECUDA, "xxh3: %s", cudaGetErrorString(e)); }
+    return PBSGPU_OK;
+}
+
+extern "C" int pbsgpu_xxh3_batch(pbsgpu_ctx *ctx, const void *base, const uint64_t *off, const uint64_t *len,
+                                 uint32_t n, uint64_t *hash_out) {
+    if (!ctx || (n && (!off || !len || !hash_out))) return PBSGPU_EINVAL;
+    Guard g(ctx);
+    if (n == 0) return PBSGPU_OK;
+    cudaStream_t st = ctx->streams[0];
+    uint64_t hi = 0;
+    for (uint32_t i = 0; i < n; i++) hi = std::max(hi, off[i] + len[i]);
+    const uint8_t *dbase = (const uint8_t *)base;
+    uint8_t *staged = nullptr;
+    if (hi && !is_device_ptr(base)) {
+        staged = (uint8_t *)ctx->dev.get(hi + 16);
+        if (!staged) return fail(ctx, PBSGPU_ENOMEM, "staging of %llu bytes failed", (unsigned long long)hi);
+        CK(cudaMemcpyAsync(staged, base, hi, cudaMemcpyHostToDevice, st));
+        dbase = staged;
+    }
+    XxhRun run;
+    int rc = xxh3_enqueue(ctx, dbase, off, len, n, st, &run);
+    if (rc == PBSGPU_OK) rc = xxh3_collect(ctx, &run, hash_out, st);
+    else cudaStreamSynchronize(st);
+    ctx->dev.put(staged);
+    return rc;
+}
+
 // flags for chunk records that are already on the host, in order
 static int apply_set(pbsgpu_set *set, pbsgpu_chunk *out, uint64_t n) {
     if (!set || n == 0) return PBSGPU_OK;
@@ -929,7 +1050,8 @@ static int apply_set(pbsgpu_set *set, pbsgpu_chunk *out, uint64_t n) {
 struct Group { uint32_t first, count; uint64_t bytes; };
 
 static int batch_host(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg, const uint8_t *base, const uint64_t *off,
-                      const uint64_t *len, uint32_t n, pbsgpu_chunk *out, uint64_t cap, uint64_t *n_out) {
+                      const uint64_t *len, uint32_t n, pbsgpu_chunk *out, uint64_t cap, uint64_t *n_out,
+                      uint64_t *xxh3_out) {
     size_t fr = 0, tot = 0;
     CK(cudaMemGetInfo(&fr, &tot));
     uint64_t stage = ctx->stage_bytes ? ctx->stage_bytes : std::min<uint64_t>(4ull << 30, fr / 16);
@@ -954,6 +1076,7 @@ static int batch_host(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg, const uint8_t *bas
         if (!bufs[b]) { for (int k = 0; k < b; k++) ctx->dev.put(bufs[k]); return fail(ctx, PBSGPU_ENOMEM, "staging buffer of %llu bytes failed", (unsigned long long)buf_bytes); }
     }
     std::vector<pbsgpu_job *> jobs(groups.size(), nullptr);
+    std::vector<XxhRun> xruns(xxh3_out ? groups.size() : 0);   // f2: per-file XXH3-64 from the same staged bytes
     std::vector<cudaEvent_t> copied(groups.size());
     for (auto &e : copied) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     int rc = PBSGPU_OK;
@@ -962,6 +1085,7 @@ static int batch_host(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg, const uint8_t *bas
     auto collect = [&](size_t gi) -> int {
         pbsgpu_job *j = jobs[gi];
         int r = job_finish(j);
+        if (xxh3_out) { int rx = xxh3_collect(ctx, &xruns[gi], xxh3_out + groups[gi].first, j->st); if (r == PBSGPU_OK) r = rx; }
         if (r == PBSGPU_OK) {
             uint64_t nch = j->h_counters[1];
             if (produced + nch > cap) overflow = true;
@@ -1000,6 +1124,7 @@ static int batch_host(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg, const uint8_t *bas
         if (rc) break;
         cudaStreamWaitEvent(j->st, copied[gi], 0);
         rc = job_enqueue(j);
+        if (rc == PBSGPU_OK && xxh3_out) rc = xxh3_enqueue(ctx, buf, goff.data(), glen.data(), g.count, j->st, &xruns[gi]);
         if (rc) { cudaStreamSynchronize(j->st); job_release(j); break; }
         jobs[gi] = j;
     }
@@ -1014,9 +1139,9 @@ static int batch_host(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg, const uint8_t *bas
     return rc;
 }
 
-extern "C" int pbsgpu_chunk_digest_batch(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg, const void *base, const uint64_t *off,
-                                         const uint64_t *len, uint32_t n, pbsgpu_set *set, pbsgpu_chunk *out,
-                                         uint64_t cap, uint64_t *n_out) {
+extern "C" int pbsgpu_chunk_digest_batch_xxh3(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg, const void *base, const uint64_t *off,
+                                              const uint64_t *len, uint32_t n, pbsgpu_set *set, pbsgpu_chunk *out,
+                                              uint64_t cap, uint64_t *n_out, uint64_t *stream_xxh3) {
     if (!ctx || (n && (!off || !len || !base)) || (cap && !out)) return PBSGPU_EINVAL;
     if (set && set->ctx != ctx) return fail(ctx, PBSGPU_EINVAL, "set belongs to another context");
     Guard g(ctx);
@@ -1028,20 +1153,29 @@ extern "C" int pbsgpu_chunk_digest_batch(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg,
         pbsgpu_job *j = nullptr;
         rc = job_create(ctx, cfg, base, off, len, n, 1, 1, &j);
         if (rc) return rc;
+        XxhRun xr;
         rc = job_enqueue(j);
+        if (rc == PBSGPU_OK && stream_xxh3) rc = xxh3_enqueue(ctx, (const uint8_t *)base, off, len, n, j->st, &xr);
         if (rc == PBSGPU_OK) rc = job_finish(j);
         if (rc == PBSGPU_OK) {
             produced = j->h_counters[1];
             if (produced > cap) rc = fail(ctx, PBSGPU_ERANGE, "output capacity %llu < %llu chunks", (unsigned long long)cap, (unsigned long long)produced);
             else if (produced) memcpy(out, j->h_out, produced * sizeof(pbsgpu_chunk));
         } else cudaStreamSynchronize(j->st);
+        if (stream_xxh3) { int rx = xxh3_collect(ctx, &xr, stream_xxh3, j->st); if (rc == PBSGPU_OK) rc = rx; }
         job_release(j);
     } else {
-        rc = batch_host(ctx, cfg, (const uint8_t *)base, off, len, n, out, cap, &produced);
+        rc = batch_host(ctx, cfg, (const uint8_t *)base, off, len, n, out, cap, &produced, stream_xxh3);
     }
     if (n_out) *n_out = produced;
     if (rc == PBSGPU_OK && set) rc = apply_set(set, out, produced);
     return rc;
+}
+
+extern "C" int pbsgpu_chunk_digest_batch(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg, const void *base, const uint64_t *off,
+                                         const uint64_t *len, uint32_t n, pbsgpu_set *set, pbsgpu_chunk *out,
+                                         uint64_t cap, uint64_t *n_out) {
+    return pbsgpu_chunk_digest_batch_xxh3(ctx, cfg, base, off, len, n, set, out, cap, n_out, nullptr);
 }
 
 extern "C" int pbsgpu_scan_batch(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg, const void *base, const uint64_t *off,

@@ -44,6 +44,9 @@ struct ScanArgs {
 };
 cudaError_t launch_scan_simple(const ScanArgs &a, cudaStream_t st);
 cudaError_t launch_scan_tuned(const ScanArgs &a, const uint32_t *rot_table /*[256][64]*/, int sm_count, cudaStream_t st);
+cudaError_t launch_scan_lanes(const ScanArgs &a, const uint32_t *rot_table, int sm_count, cudaStream_t st);
+uint64_t scan_lanes_super_bytes();
+uint32_t scan_lanes_steps();
 cudaError_t launch_build_rot_table(const uint32_t *table, uint32_t *rot_table, cudaStream_t st);
 size_t scan_tuned_smem_bytes();
 
@@ -112,6 +115,14 @@ cudaError_t launch_crc32_tiled(const uint8_t *base, const uint64_t *off, const u
                                uint32_t *part_crc, uint32_t *out, int sm_count, cudaStream_t st);
 uint64_t crc_region_bytes();
 size_t crc_tables_bytes();
+// K7 (xxh3.cu)
+size_t xxh3_tables_bytes();
+void xxh3_fill_tables_host(void *dst);
+cudaError_t launch_xxh3_pass(const uint8_t *base, const uint64_t *off, const uint64_t *len, const uint64_t *first, uint32_t n,
+                             uint64_t total, uint64_t win_lo, uint64_t win, const void *tab, uint64_t *S, uint64_t *state,
+                             uint64_t *out, cudaStream_t st);
+cudaError_t launch_xxh3_small(const uint8_t *base, const uint64_t *off, const uint64_t *len, uint32_t n, const void *tab,
+                              uint64_t *out, cudaStream_t st);
 void crc_fill_tables_host(void *dst);
 uint64_t crc_wb_bytes();
 

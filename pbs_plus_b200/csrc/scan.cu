@@ -273,6 +273,217 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 1) k_scan_tuned(ScanArgs a
     }
 }
 
+// ============================================================================
+// Lane-contiguous variant (k_scan_lanes).  In k_scan_tuned a lane's 272 B span of the next tile is not
+// adjacent to its span of this tile, so every tile pays a 64 B warm-up per lane (23.5 % extra work).
+// Here a warp owns a SUPER-TILE of 32 x 2 KiB: lane L owns the contiguous bytes [L*2048, (L+1)*2048) and
+// walks them in 8 steps of 256 B; each step brings 32 per-lane 256 B pieces by TMA (tools/tma_piece_probe:
+// same HBM rate as one contiguous 8 KiB copy), and the lane's 64-entry Q ring simply carries over from
+// step to step -- the warm-up is paid once per 2 KiB (3 %).  A stream's tail (< 64 KiB) and streams whose
+// start is not 16 B aligned keep using plain 8704 B tiles inside the same kernel.
+// tile_first[] then counts STEPS: 8 per super-tile (floor(len / 64 KiB) of them), then one per plain tile.
+// ============================================================================
+constexpr int LS_R = 2048;                    // bytes per lane per super-tile
+constexpr int LS_PIECE = 256;
+constexpr int LS_STEPS = LS_R / LS_PIECE;     // 8
+constexpr int LS_SUPER = 32 * LS_R;           // 64 KiB
+constexpr int LS_HALO_STRIDE = 80;            // 64 B halo + 16 B pad: conflict-free LDS.128 (5 quads)
+constexpr int LS_SMEM = ROT_BYTES + WARPS_PER_CTA * (2 * BUF_STRIDE + 32 * LS_HALO_STRIDE) + WARPS_PER_CTA * 2 * 8;
+
+uint64_t scan_lanes_super_bytes() { return LS_SUPER; }
+uint32_t scan_lanes_steps() { return LS_STEPS; }
+
+struct StepInfo {
+    uint32_t stream;
+    uint32_t kind;        // 0 = plain tile, 1 = step of a super-tile
+    uint32_t valid;       // plain tile: bytes of the stream in the tile
+    uint32_t k;           // super-tile: step 0..LS_STEPS-1
+    uint64_t stream_pos;  // stream offset of the tile / super-tile
+};
+
+// Exact walk of one lane's 256 B piece (slow path of k_scan_lanes).  The piece is in shared memory; the 64 bytes
+// before it left shared memory a step ago, so they come back from global memory (L2) as four 16 B loads.
+__device__ __noinline__ void piece_exact(const ScanArgs &a, const uint8_t *piece, const uint32_t *rot, uint32_t lane,
+                                         uint32_t stream, const uint8_t *d, uint64_t start) {
+    uint4 hv[4];
+    if (start >= 64) {
+        const uint4 *g = (const uint4 *)(d + start - 64);   // stream start and `start` are multiples of 16
+#pragma unroll
+        for (int i = 0; i < 4; i++) hv[i] = g[i];
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; i++) hv[i] = make_uint4(0, 0, 0, 0);
+    }
+    const uint8_t *halo = (const uint8_t *)hv;
+    uint32_t h = 0;
+    for (int p = 0; p < 64; p++) h = rotl32(h, 1) ^ rotl32(rot[halo[p] * ROT_SLOTS + lane], lane);
+    for (int p = 0; p < LS_PIECE; p++) {
+        const uint32_t leave = p < 64 ? halo[p] : piece[p - 64];
+        h = rotl32(h, 1) ^ rotl32(rot[piece[p] * ROT_SLOTS + lane], lane) ^ rotl32(rot[leave * ROT_SLOTS + lane], lane);
+        const uint64_t pos = start + (uint32_t)p;
+        if (pos >= 63 && (h & a.mask) >= a.break_min) emit_candidate(a, stream, pos);
+    }
+}
+
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 1) k_scan_lanes(ScanArgs a, const uint32_t *__restrict__ rot_g) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint32_t *rot = (uint32_t *)smem;
+    const uint8_t *rotb = smem;
+    {
+        const uint4 *src = (const uint4 *)rot_g;
+        uint4 *dst = (uint4 *)smem;
+        for (int i = threadIdx.x; i < ROT_BYTES / 16; i += blockDim.x) dst[i] = src[i];
+    }
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t *buf0 = smem + ROT_BYTES + warp * (2 * BUF_STRIDE + 32 * LS_HALO_STRIDE);
+    uint8_t *halo_buf = buf0 + 2 * BUF_STRIDE;
+    uint64_t *bars = (uint64_t *)(smem + ROT_BYTES + WARPS_PER_CTA * (2 * BUF_STRIDE + 32 * LS_HALO_STRIDE)) + warp * 2;
+    const uint32_t bar_s[2] = {smem_u32(&bars[0]), smem_u32(&bars[1])};
+    if (lane == 0) {
+        mbar_init(bar_s[0], 1);
+        mbar_init(bar_s[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const uint64_t gw = (uint64_t)blockIdx.x * WARPS_PER_CTA + warp, nw = (uint64_t)gridDim.x * WARPS_PER_CTA;
+    auto n_super_of = [&](uint32_t sc) -> uint64_t {
+        return (((uintptr_t)(a.base + a.off[sc])) & 15) == 0 ? a.len[sc] / LS_SUPER : 0;
+    };
+    // warps split the step list evenly, but a split inside a super-tile moves back to the super-tile's step 0
+    auto round_unit = [&](uint64_t x) -> uint64_t {
+        if (x >= a.total_tiles) return a.total_tiles;
+        const uint32_t sc = find_stream(a.tile_first, a.n_streams, x);
+        const uint64_t j = x - a.tile_first[sc];
+        return j < n_super_of(sc) * LS_STEPS ? x - (j % LS_STEPS) : x;
+    };
+    const uint64_t u0 = round_unit(a.total_tiles * gw / nw), u1 = round_unit(a.total_tiles * (gw + 1) / nw);
+    if (u0 >= u1) return;
+
+    const uint32_t m21 = a.mask & ~3u;
+    uint32_t M[32];
+#pragma unroll
+    for (int k = 0; k < 32; k++) M[k] = rotr32(m21, (k + lane) & 31);
+    const uint32_t laneoff = lane * 4;
+
+    // step cursor: tile_first[] counts STEPS (a super-tile is LS_STEPS of them, a plain tile one)
+    uint32_t s = find_stream(a.tile_first, a.n_streams, u0);
+    uint64_t s_first = a.tile_first[s], s_next = a.tile_first[s + 1];
+    uint64_t s_ns = n_super_of(s);
+    uint64_t u = u0;
+    auto next_step = [&](StepInfo &st) -> bool {
+        if (u >= u1) return false;
+        while (u >= s_next) { s++; s_first = s_next; s_next = a.tile_first[s + 1]; s_ns = n_super_of(s); }
+        const uint64_t j = u - s_first;
+        st.stream = s;
+        if (j < s_ns * LS_STEPS) {
+            st.kind = 1; st.k = (uint32_t)(j % LS_STEPS); st.valid = 0; st.stream_pos = (j / LS_STEPS) * LS_SUPER;
+        } else {
+            st.kind = 0; st.k = 0;
+            st.stream_pos = s_ns * LS_SUPER + (j - s_ns * LS_STEPS) * WARP_TILE;
+            const uint64_t rem = a.len[s] - st.stream_pos;
+            st.valid = rem < (uint64_t)WARP_TILE ? (uint32_t)rem : (uint32_t)WARP_TILE;
+        }
+        u++;
+        return true;
+    };
+    auto issue = [&](const StepInfo &st, int b) {
+        uint8_t *buf = buf0 + b * BUF_STRIDE;
+        const uint8_t *sbase = a.base + a.off[st.stream];
+        if (st.kind == 1) {
+            const uint64_t lane_start = st.stream_pos + (uint64_t)lane * LS_R;
+            const bool first_of_stream = st.k == 0 && lane_start == 0;      // only lane 0 of the stream's first super-tile
+            if (st.k == 0 && first_of_stream) {
+                uint32_t *hz = (uint32_t *)(halo_buf + lane * LS_HALO_STRIDE);
+#pragma unroll
+                for (int i = 0; i < 16; i++) hz[i] = 0;                     // zero halo (positions < 63 are never reported)
+            }
+            const uint32_t any_first = __ballot_sync(0xffffffffu, first_of_stream);
+            uint32_t bytes = 32 * LS_PIECE + (st.k == 0 ? (32 - __popc(any_first)) * 64 : 0);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // this lane's earlier reads of the buffer
+            __syncwarp();
+            if (lane == 0) mbar_arrive_expect_tx(bar_s[b], bytes);
+            __syncwarp();
+            tma_bulk_g2s(smem_u32(buf + lane * LANE_SPAN), sbase + lane_start + (uint64_t)st.k * LS_PIECE, LS_PIECE, bar_s[b]);
+            if (st.k == 0 && !first_of_stream)
+                tma_bulk_g2s(smem_u32(halo_buf + lane * LS_HALO_STRIDE), sbase + lane_start - 64, 64, bar_s[b]);
+        } else {
+            const uint8_t *src = sbase + st.stream_pos;
+            uint32_t halo = st.stream_pos ? HALO : 0;
+            uint32_t bytes = halo + st.valid;
+            const uint8_t *src0 = src - halo;
+            uint8_t *dst0 = buf + (HALO - halo);
+            if (!halo && lane < 16) ((uint32_t *)buf)[lane] = 0;
+            if ((((uintptr_t)src0) & 15) == 0) {
+                uint32_t bulk = bytes & ~15u;
+                for (uint32_t i = bulk + lane; i < bytes; i += 32) dst0[i] = src0[i];
+                __syncwarp();
+                if (lane == 0) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_arrive_expect_tx(bar_s[b], bulk);
+                    if (bulk) tma_bulk_g2s(smem_u32(dst0), src0, bulk, bar_s[b]);
+                }
+            } else {
+                for (uint32_t i = lane; i < bytes; i += 32) dst0[i] = src0[i];
+                __syncwarp();
+                if (lane == 0) mbar_arrive_expect_tx(bar_s[b], 0);
+            }
+        }
+    };
+
+    uint32_t Q[64];
+    uint32_t q = 0;
+    StepInfo cur, nxt;
+    bool have = next_step(cur);
+    if (have) issue(cur, 0);
+    for (uint64_t n = 0; have; n++) {
+        const int b = (int)(n & 1);
+        const bool have_next = next_step(nxt);
+        if (have_next) issue(nxt, b ^ 1);
+        mbar_wait(bar_s[b], (uint32_t)((n >> 1) & 1));
+        const uint8_t *buf = buf0 + b * BUF_STRIDE;
+        uint32_t acc = 1;
+        if (cur.kind == 1) {
+            const uint4 *data = (const uint4 *)(buf + lane * LANE_SPAN);
+            if (cur.k == 0) {
+                q = 0;
+                lane_block<false, 4>((const uint4 *)(halo_buf + lane * LS_HALO_STRIDE), rotb, laneoff, Q, M, q, acc);
+            }
+#pragma unroll 1
+            for (int it = 0; it < 4; it++) lane_block<true, 4>(data + it * 4, rotb, laneoff, Q, M, q, acc);
+            if (!acc)
+                piece_exact(a, buf + lane * LANE_SPAN, rot, lane, cur.stream, a.base + a.off[cur.stream],
+                            cur.stream_pos + (uint64_t)lane * LS_R + (uint64_t)cur.k * LS_PIECE);
+        } else {
+            TileInfo ti;
+            ti.stream = cur.stream; ti.valid = cur.valid; ti.stream_pos = cur.stream_pos;
+            if (cur.valid == WARP_TILE) {
+                const uint4 *data = (const uint4 *)(buf + lane * LANE_SPAN);
+                q = 0;
+                lane_block<false, 4>(data, rotb, laneoff, Q, M, q, acc);
+#pragma unroll 1
+                for (int it = 1; it <= 4; it++) lane_block<true, 4>(data + it * 4, rotb, laneoff, Q, M, q, acc);
+                lane_block<true, 1>(data + 20, rotb, laneoff, Q, M, q, acc);
+                if (!acc) lane_exact(a, buf, rot, lane, ti);
+            } else {
+                lane_exact(a, buf, rot, lane, ti);
+            }
+        }
+        __syncwarp();
+        cur = nxt;
+        have = have_next;
+    }
+}
+
+cudaError_t launch_scan_lanes(const ScanArgs &a, const uint32_t *rot_table, int sm_count, cudaStream_t st) {
+    if (a.total_tiles == 0) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(k_scan_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, LS_SMEM);
+    if (e != cudaSuccess) return e;
+    uint64_t want = (a.total_tiles + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    unsigned grid = (unsigned)(want < (uint64_t)sm_count ? want : (uint64_t)sm_count);
+    k_scan_lanes<<<grid, WARPS_PER_CTA * 32, LS_SMEM, st>>>(a, rot_table);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_scan_tuned(const ScanArgs &a, const uint32_t *rot_table, int sm_count, cudaStream_t st) {
     if (a.total_tiles == 0) return cudaSuccess;
     // per launch (cheap): the attribute is per device and a process may drive several devices

@@ -130,6 +130,20 @@ class Engine:
             digest_set._h if digest_set is not None else None, out.ctypes.data, cap, C.byref(n_out)))
         return out[: n_out.value]
 
+    def chunk_digest_batch_xxh3(self, cfg: Cfg, base, off, length, digest_set: "DigestSet | None" = None):
+        """chunk_digest_batch plus the XXH3-64 of every stream from the same staged bytes (f2: the per-file
+        hash of emitBackedFile, reference commit.go:717-725).  Returns (chunks, xxh3[n] uint64)."""
+        o, l = self._offlen(off, length)
+        cap = self._chunk_cap(cfg, l)
+        out = np.zeros(cap, dtype=CHUNK_DTYPE)
+        hashes = np.zeros(len(o), dtype=np.uint64)
+        n_out = C.c_uint64()
+        keep = base
+        self._ck(self._L.pbsgpu_chunk_digest_batch_xxh3(
+            self._h, C.byref(cfg), _ptr(keep), o.ctypes.data, l.ctypes.data, len(o),
+            digest_set._h if digest_set is not None else None, out.ctypes.data, cap, C.byref(n_out), hashes.ctypes.data))
+        return out[: n_out.value], hashes
+
     def chunk_digest_streams(self, cfg: Cfg, streams: Iterable[np.ndarray], digest_set=None) -> np.ndarray:
         """Convenience for host streams that are separate arrays: packs them and calls the batch ABI."""
         arrs = [np.ascontiguousarray(s, dtype=np.uint8) for s in streams]
@@ -168,6 +182,14 @@ class Engine:
         out = np.zeros((len(o), 32), dtype=np.uint8)
         self._ck(self._L.pbsgpu_sha256_batch(self._h, _ptr(base), o.ctypes.data, l.ctypes.data, len(o),
                                              out.ctypes.data))
+        return out
+
+    # -- f2: per-file content hash of the commit walk ---------------------------------------------
+    def xxh3_batch(self, base, off, length) -> np.ndarray:
+        """XXH3-64 (seed 0) of n byte ranges (host or device base) on the GPU; uint64[n]."""
+        o, l = self._offlen(off, length)
+        out = np.zeros(len(o), dtype=np.uint64)
+        self._ck(self._L.pbsgpu_xxh3_batch(self._h, _ptr(base), o.ctypes.data, l.ctypes.data, len(o), out.ctypes.data))
         return out
 
     # -- f3: DataBlob checksums --------------------------------------------------------------

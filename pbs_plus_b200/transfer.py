@@ -48,6 +48,9 @@ class DedupWriter:
     upload: Callable[[bytes, bytes], None] | None = None   # (digest, chunk bytes) for NEW chunks
     batch_bytes: int = 1 << 30
     index: list[IndexRecord] = field(default_factory=list)
+    # relPath -> XXH3-64 of the file as uploaded: commitWalkState.backedHashes (commit.go:187, :725), computed on the
+    # GPU from the same staged bytes instead of through an io.TeeReader on the host
+    backed_hashes: dict[str, int] = field(default_factory=dict)
     _pending: list[tuple[Entry, np.ndarray]] = field(default_factory=list)
     _pending_bytes: int = 0
     _finished: bool = False
@@ -71,7 +74,9 @@ class DedupWriter:
         if not self._pending:
             return
         entries, arrs = zip(*self._pending)
-        rec = self.engine.chunk_digest_streams(self.config, arrs, self.known)
+        rec, hashes = self._batch(arrs)
+        for e, h in zip(entries, hashes):
+            self.backed_hashes[e.Path] = int(h)
         for r in rec:
             i = int(r["stream"])
             known = bool(r["flags"] & CHUNK_KNOWN)
@@ -86,6 +91,18 @@ class DedupWriter:
                     self.upload(bytes(r["digest"]), arrs[i][s:e].tobytes())
                 starts[i] = e
         self._pending, self._pending_bytes = [], 0
+
+    def _batch(self, arrs):
+        lens = np.array([len(a) for a in arrs], dtype=np.uint64)
+        offs = np.zeros(len(arrs), dtype=np.uint64)
+        pos = 0
+        for i, a in enumerate(arrs):
+            offs[i] = pos
+            pos += (len(a) + 255) & ~255
+        buf = np.zeros(max(pos, 1), dtype=np.uint8)
+        for a, o in zip(arrs, offs):
+            buf[int(o): int(o) + len(a)] = a
+        return self.engine.chunk_digest_batch_xxh3(self.config, buf, offs, lens, self.known)
 
     def Finish(self) -> list[IndexRecord]:
         self.Flush()

@@ -1,7 +1,7 @@
 // tests/cxx/driver.cpp -- C++ caller of the C ABI through the host mirror (include/pbsgpu.hpp),
 // standing in for the Go caller that cannot be built here.  Reads files named on the command
 // line, pushes them through transfer::DedupWriter twice (second pass: everything is known) and
-// prints one line per chunk:  <path> <end_off> <digest hex> <known>.  tests/test_gpu_parity.py
+// prints one line per chunk:  <pass> <path> <end_off> <digest hex> <known>, and `xxh3 <path> <hex>` per file.  tests/test_gpu_parity.py
 // compares the output with the oracle.
 #include <cstdio>
 #include <string>
@@ -29,6 +29,8 @@ int main(int argc, char **argv) {
                 for (int k = 0; k < 32; k++) std::printf("%02x", r.digest[k]);
                 std::printf(" %d\n", r.known ? 1 : 0);
             }
+            if (pass == 0)   // backedHashes (commit.go:725): XXH3-64 per file from the same staged bytes
+                for (auto &kv : w.BackedHashes()) std::printf("xxh3 %s %016llx\n", kv.first.c_str(), (unsigned long long)kv.second);
         }
         try { pbsgpu::buzhash::NewConfig(3000); std::printf("ERR expected\n"); return 3; }
         catch (const pbsgpu::Error &e) { std::printf("config-error %d\n", e.code); }

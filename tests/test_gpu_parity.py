@@ -384,6 +384,7 @@ def test_dedup_writer_mirror_of_the_reference_surface(eng):
     for d, b in uploaded.items():
         assert hashlib.sha256(b).digest() == d
     assert len(uploaded) == len({r.digest for r in index})
+    assert w.backed_hashes == {k: _xxh3_ref(v) for k, v in files.items()}      # commit.go:725 ow.backedHashes
 
 
 def test_cxx_host_mirror_driver(tmp_path):
@@ -403,7 +404,9 @@ def test_cxx_host_mirror_driver(tmp_path):
     lines = out.stdout.strip().splitlines()
     assert lines[-1] == "config-error -22"
     ref = oracle.chunk_digest_streams(oracle.config(16 << 10), list(datas.values()))
-    rows = [l.split() for l in lines[:-1]]
+    rows = [l.split() for l in lines[:-1] if not l.startswith("xxh3 ")]
+    xx = {l.split()[1]: int(l.split()[2], 16) for l in lines if l.startswith("xxh3 ")}
+    assert xx == {p: _xxh3_ref(v) for p, v in zip(paths, datas.values())}      # backedHashes mirror (commit.go:725)
     for ps in (0, 1):
         got = [(r[1], int(r[2]), r[3], int(r[4])) for r in rows if int(r[0]) == ps]
         assert [(g[1], g[2]) for g in got] == [(int(r["end_off"]), bytes(r["digest"]).hex()) for r in ref]
@@ -559,3 +562,107 @@ def test_structured_data_kinds_match_oracle(eng, torch, variant):
             assert rec.tobytes() == ref.tobytes(), (avg, variant)
     finally:
         eng.set_kernel_variant(0)
+
+
+# ---- K1 variant: lane-contiguous scan kernel (PBSGPU_SCAN_LANES=1, off by default) ---------------------------------
+def _engine_with_env(env):
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        return pg.Engine(0)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                del os.environ[k]
+            else:
+                os.environ[k] = v
+
+
+def test_scan_lanes_variant_matches_oracle(torch):
+    """k_scan_lanes (64 KiB super-tiles, per-lane TMA pieces) must give the boundaries k_scan_tuned gives: streams
+    with several super-tiles, tails, a stream below one super-tile, misaligned streams (plain-tile path only)."""
+    e = _engine_with_env({"PBSGPU_SCAN_LANES": "1"})
+    try:
+        arrs = [rnd(n, 900 + i) for i, n in enumerate([65536 * 5 + 777, 65536, 65535, 65537, 3 * 65536 + 8704, 100, 0,
+                                                       1_000_003, 65536 * 2])]
+        for avg in (256, 4096, 1 << 16):
+            cfg_o = oracle.config(avg)
+            want, want_first = oracle_ends(cfg_o, arrs)
+            for align, lead in ((256, 0), (1, 3), (16, 16)):
+                buf, off, ln = pack(arrs, align=align, lead=lead)
+                ends, first = e.scan_batch(pg.make_config(avg), to_dev(torch, buf), off, ln)
+                assert ends.tolist() == want and first.tolist() == want_first, (avg, align, lead)
+        big = rnd(40_000_000, 950)
+        rec = e.chunk_digest_batch(pg.make_config(1 << 16), to_dev(torch, big), [0], [len(big)])
+        assert rec.tobytes() == oracle.chunk_digest(oracle.config(1 << 16), big).tobytes()
+    finally:
+        e.close()
+
+
+# ---- f2: XXH3-64 of the commit walk (K7) ----------------------------------------------------------------------------
+def _xxh3_ref(a):
+    try:
+        import xxhash                      # independent implementation (libxxhash binding)
+        return xxhash.xxh3_64_intdigest(np.ascontiguousarray(a).tobytes())
+    except ImportError:                    # the oracle restatement is pinned against it in the CPU suite
+        return oracle.xxh3_64(a)
+
+
+def test_xxh3_every_short_length_and_alignment(eng, torch):
+    data = rnd(4096, 1200)
+    lens = list(range(0, 1300)) + [2047, 2048, 2049, 3072, 3073, 4000]
+    for lead in (0, 1, 5, 16):
+        off = np.array([lead + (i % 7) for i in range(len(lens))], dtype=np.uint64)
+        ln = np.array(lens, dtype=np.uint64)
+        ok = off + ln <= len(data)
+        off, ln2 = off[ok], ln[ok]
+        want = np.array([_xxh3_ref(data[int(o): int(o + l)]) for o, l in zip(off, ln2)], dtype=np.uint64)
+        got_dev = eng.xxh3_batch(to_dev(torch, data), off, ln2)
+        got_host = eng.xxh3_batch(data, off, ln2)
+        assert got_dev.tolist() == want.tolist(), lead
+        assert got_host.tolist() == want.tolist(), lead
+        assert [oracle.xxh3_64(data[int(o): int(o + l)]) for o, l in zip(off[:300], ln2[:300])] == want[:300].tolist()
+
+
+def test_xxh3_long_streams_aligned_and_not(eng, torch):
+    sizes = [1 << 20, (1 << 20) + 1, (1 << 20) - 1, 5_000_003, 64 * 1024, 1025, 1024, 241, 240, 0, 3 << 20, 777_777]
+    arrs = [rnd(n, 1300 + i) for i, n in enumerate(sizes)]
+    want = [_xxh3_ref(a) for a in arrs]
+    for align, lead in ((256, 0), (1, 0), (1, 7), (16, 16)):
+        buf, off, ln = pack(arrs, align=align, lead=lead)
+        assert eng.xxh3_batch(to_dev(torch, buf), off, ln).tolist() == want, (align, lead)
+    buf, off, ln = pack(arrs)
+    assert eng.xxh3_batch(buf, off, ln).tolist() == want          # host base: staged by the library
+
+
+def test_xxh3_is_pass_invariant(torch):
+    """A tiny per-pass block budget forces many passes with carried chain state: same hashes."""
+    e = _engine_with_env({"PBSGPU_XXH3_CAP_BLOCKS": "37"})
+    try:
+        sizes = [300_000, 5, 70_001, 1 << 20, 0, 2048, 123_456, 1025]
+        arrs = [rnd(n, 1400 + i) for i, n in enumerate(sizes)]
+        buf, off, ln = pack(arrs, align=16)
+        assert e.xxh3_batch(to_dev(torch, buf), off, ln).tolist() == [_xxh3_ref(a) for a in arrs]
+    finally:
+        e.close()
+
+
+def test_fused_batch_returns_chunks_and_file_xxh3(torch):
+    """pbsgpu_chunk_digest_batch_xxh3: the chunk records of the plain call plus every stream's XXH3-64, from device
+    input and from host input staged in several groups."""
+    e = _engine_with_env({"PBSGPU_STAGE_BYTES": str(1 << 20)})
+    try:
+        arrs = [rnd(n, 1500 + i) for i, n in enumerate([400_000, 0, 900_000, 1_500_000, 10, 700_000, 333, 1024])]
+        want_rec = oracle.chunk_digest_streams(oracle.config(4096), arrs).tobytes()
+        want_h = [_xxh3_ref(a) for a in arrs]
+        buf, off, ln = pack(arrs)
+        cfg = pg.make_config(4096)
+        rec, h = e.chunk_digest_batch_xxh3(cfg, buf, off, ln)                      # host base
+        assert rec.tobytes() == want_rec and h.tolist() == want_h
+        rec, h = e.chunk_digest_batch_xxh3(cfg, to_dev(torch, buf), off, ln)       # device base
+        assert rec.tobytes() == want_rec and h.tolist() == want_h
+        ds = e.digest_set()
+        rec, h = e.chunk_digest_batch_xxh3(cfg, to_dev(torch, buf), off, ln, ds)   # with the known-set
+        assert h.tolist() == want_h and len(ds) == len({bytes(r["digest"]) for r in rec})
+    finally:
+        e.close()

@@ -26,6 +26,11 @@ class OracleEngine:
             rec["flags"] = digest_set.insert(rec["digest"]) * CHUNK_KNOWN
         return rec
 
+    def chunk_digest_batch_xxh3(self, cfg, buf, off, length, digest_set=None):
+        streams = [np.asarray(buf[int(o): int(o + l)]) for o, l in zip(off, length)]
+        rec = self.chunk_digest_streams(cfg, streams, digest_set)
+        return rec, np.array([oracle.xxh3_64(s) for s in streams], dtype=np.uint64)
+
     def digest_set(self, hint=0):
         class S:
             def __init__(s): s.s = oracle.DigestSet()
@@ -66,6 +71,7 @@ def test_dedup_writer_flow_index_order_and_upload_only_new():
     assert all(hashlib.sha256(b).digest() == d for d, b in uploaded)
     assert {d for d, _ in uploaded} == {r.digest for r in idx}      # every distinct chunk uploaded exactly once
     assert len(uploaded) == len({r.digest for r in idx})
+    assert w.backed_hashes == {name: oracle.xxh3_64(data) for name, data in files}   # ow.backedHashes, commit.go:725
     with pytest.raises(RuntimeError):
         w.WriteEntry(transfer.Entry("late", 1), b"x")
 

@@ -193,3 +193,27 @@ def test_golden_vectors():
         assert rec["end_off"].tolist() == g["cuts"]
         assert [bytes(x).hex() for x in rec["digest"]] == g["digests"]
         assert hashlib.sha256(data.tobytes()).hexdigest() == g["data_sha256"]
+
+
+def test_xxh3_64_is_pinned_against_libxxhash():
+    """Row f2 (commit.go:717-725): the oracle's XXH3-64 restatement equals the independent python-xxhash binding
+    for every length class (0, 1-3, 4-8, 9-16, 17-128, 129-240, > 240 with and without full blocks) and for
+    long inputs at odd alignments; plus the published empty-input value."""
+    xxhash = pytest.importorskip("xxhash")
+    rng = np.random.default_rng(1)
+    buf = rng.integers(0, 256, 6000, dtype=np.uint8)
+    assert oracle.xxh3_64(b"") == 0x2D06800538D394C2
+    for n in range(0, 2101):
+        assert oracle.xxh3_64(buf[:n]) == xxhash.xxh3_64_intdigest(buf[:n].tobytes()), n
+    for n in (2047, 2048, 2049, 4096, 4097, 5999):
+        for lead in (0, 1, 3):
+            v = buf[lead:lead + n]
+            assert oracle.xxh3_64(v) == xxhash.xxh3_64_intdigest(v.tobytes()), (n, lead)
+    big = rng.integers(0, 256, (3 << 20) + 77, dtype=np.uint8)
+    for lead in (0, 1, 7):
+        assert oracle.xxh3_64(big[lead:]) == xxhash.xxh3_64_intdigest(big[lead:].tobytes())
+    # streaming use (xxh3.New(); io.Copy; Sum64) equals the one-shot value by the specification
+    h = xxhash.xxh3_64()
+    for i in range(0, len(big), 65536):
+        h.update(big[i:i + 65536].tobytes())
+    assert h.intdigest() == oracle.xxh3_64(big)
