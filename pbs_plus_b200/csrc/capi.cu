@@ -1298,7 +1298,6 @@ extern "C" int pbsgpu_stream_open(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg, pbsgpu
 
 // collect finished windows (all of them if block) in order
 static int stream_collect(pbsgpu_stream *s, bool block) {
-    pbsgpu_ctx *ctx = s->ctx;
     while (!s->inflight.empty()) {
         StreamJob sj = s->inflight.front();
         if (!block) {

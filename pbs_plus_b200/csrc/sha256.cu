@@ -443,7 +443,6 @@ cudaError_t launch_sha_tuned(const ShaArgs &a, int sm_count, cudaStream_t st) {
 // (part 1) each CTA therefore also asks for more than half an SM's shared memory, which caps it at
 // ONE CTA per SM and forces the spread; the throughput kernel uses no shared memory and still
 // co-resides.
-constexpr int SPLIT_SPREAD_SMEM = 112 * 1024;
 template <int PM, int CM>
 static cudaError_t launch_split_t(const ShaArgs &a, const Opq &o, unsigned blocks, cudaStream_t st) {
     size_t dyn = 0;
