@@ -666,3 +666,16 @@ def test_fused_batch_returns_chunks_and_file_xxh3(torch):
         assert h.tolist() == want_h and len(ds) == len({bytes(r["digest"]) for r in rec})
     finally:
         e.close()
+
+
+def test_xxh3_golden_vectors_through_the_c_abi(eng, torch):
+    """K7 against the committed libxxhash vectors (independent of python-xxhash being installed on the box)."""
+    recs = [json.loads(l) for l in (GOLDEN / "xxh3_libxxhash.jsonl").read_text().splitlines()]
+    arrs, want = [], []
+    for r in recs:
+        c = oracle.corpus(seed=r["seed"], file_len=max(r["len"] + r["lead"], 1), block_len=r["block_len"])
+        arrs.append(oracle.corpus_file(c, 0)[r["lead"]: r["lead"] + r["len"]])
+        want.append(int(r["xxh3_64"], 16))
+    for align in (256, 1):
+        buf, off, ln = pack(arrs, align=align)
+        assert eng.xxh3_batch(to_dev(torch, buf), off, ln).tolist() == want, align

@@ -1,6 +1,7 @@
 """Property-based checks (hypothesis) of the oracle's chunker: the invariants that must hold for ANY input
 and that the GPU tests then inherit by comparing against this oracle."""
 import numpy as np
+import pytest
 from hypothesis import given, settings, strategies as st
 
 import oracle
@@ -70,3 +71,11 @@ def test_an_edit_only_moves_nearby_cuts(avg, d, pos, val):
     if common:                                                 # after the first common cut everything agrees again
         c = common[0]
         assert [e for e in a if e >= c] == [e for e in b if e >= c]
+
+
+@settings(max_examples=200, deadline=None)
+@given(st.binary(min_size=0, max_size=5000), st.integers(min_value=0, max_value=7))
+def test_xxh3_oracle_equals_libxxhash_on_arbitrary_bytes(data, lead):
+    xxhash = pytest.importorskip("xxhash")
+    buf = np.frombuffer(b"\x00" * lead + data, dtype=np.uint8)[lead:]
+    assert oracle.xxh3_64(buf) == xxhash.xxh3_64_intdigest(data)
