@@ -206,6 +206,27 @@ func (b *Batch) flush(known *KnownSet, withHashes bool) ([]Chunk, []uint64, erro
 	return res, hs, nil
 }
 
+// FileHashes returns the XXH3-64 of every queued file WITHOUT chunking: the verify pass of the commit
+// (verifyBackedFileHashes, commit.go:957-976) re-reads the backed files into the staging buffer with
+// WriteEntryReader and compares these values with ow.backedHashes.  The queue is cleared.
+func (b *Batch) FileHashes() ([]uint64, error) {
+	n := len(b.off)
+	if n == 0 {
+		return nil, nil
+	}
+	hashes := make([]C.uint64_t, n)
+	rc := C.pbsgpu_xxh3_batch(b.e.ctx, b.buf, &b.off[0], &b.ln[0], C.uint32_t(n), &hashes[0])
+	if err := b.e.err(rc); err != nil {
+		return nil, err
+	}
+	res := make([]uint64, n)
+	for i := range hashes {
+		res[i] = uint64(hashes[i])
+	}
+	b.off, b.ln, b.fill = b.off[:0], b.ln[:0], 0
+	return res, nil
+}
+
 func (b *Batch) Close() { C.pbsgpu_host_free(b.e.ctx, b.buf) }
 
 // BuildDidx renders the dynamic-index image (<name>.ppxar.didx, commit.go:321-322) for chunks in

@@ -119,3 +119,47 @@ def NewRemoteDedupSplitArchiveWriter(engine: Engine, config: Cfg, known: DigestS
             known = engine.digest_set()
         known.seed_didx(orig_payload_idx)
     return DedupWriter(engine, config, known, upload)
+
+
+def verifyBackedFileHashes(engine: Engine, open_file: Callable[[str], BinaryIO], hashes: dict[str, int],
+                           batch_bytes: int = 1 << 30) -> None:
+    """Mirror of verifyBackedFileHashes (reference internal/pxarmount/commit.go:957-976): every backed file is read
+    again and its XXH3-64 must equal the value recorded at upload time.  The reference hashes on the host through a
+    64 KiB copy buffer, one file at a time; here the files are packed into batches and hashed by ONE
+    pbsgpu_xxh3_batch call each.  Errors keep the reference's wording:
+    `open backed file "<p>" for verification: ...` and `backed file "<p>" content hash differs`."""
+    names: list[str] = []
+    arrs: list[np.ndarray] = []
+    held = 0
+
+    def flush() -> None:
+        nonlocal names, arrs, held
+        if not names:
+            return
+        lens = np.array([len(a) for a in arrs], dtype=np.uint64)
+        offs = np.zeros(len(arrs), dtype=np.uint64)
+        pos = 0
+        for i, a in enumerate(arrs):
+            offs[i] = pos
+            pos += (len(a) + 255) & ~255
+        buf = np.zeros(max(pos, 1), dtype=np.uint8)
+        for a, o in zip(arrs, offs):
+            buf[int(o): int(o) + len(a)] = a
+        got = engine.xxh3_batch(buf, offs, lens)
+        for name, h in zip(names, got):
+            if int(h) != hashes[name]:
+                raise IOError(f'backed file "{name}" content hash differs')
+        names, arrs, held = [], [], 0
+
+    for rel in hashes:
+        try:
+            with open_file(rel) as f:
+                data = f.read()
+        except OSError as ex:
+            raise IOError(f'open backed file "{rel}" for verification: {ex}') from ex
+        names.append(rel)
+        arrs.append(np.frombuffer(data, dtype=np.uint8))
+        held += len(data)
+        if held >= batch_bytes:
+            flush()
+    flush()

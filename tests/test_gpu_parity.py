@@ -679,3 +679,21 @@ def test_xxh3_golden_vectors_through_the_c_abi(eng, torch):
     for align in (256, 1):
         buf, off, ln = pack(arrs, align=align)
         assert eng.xxh3_batch(to_dev(torch, buf), off, ln).tolist() == want, align
+
+
+def test_verify_backed_file_hashes_on_the_gpu(eng, tmp_path):
+    """The commit's second phase (commit.go:957-976) through the engine: hashes recorded by the fused batch call
+    verify, a changed file is reported with the reference's message."""
+    import io
+    files = {"x.bin": rnd(500_000, 1601), "y.bin": rnd(77, 1602), "z.bin": rnd(0, 1603)}
+    w = pg.transfer.DedupWriter(eng, pg.buzhash.NewConfigBytes(4096))
+    for k, v in files.items():
+        (tmp_path / k).write_bytes(v.tobytes())
+        w.WriteEntryReader(pg.transfer.Entry(k, len(v)), io.BytesIO(v.tobytes()), len(v))
+    w.Finish()
+    opener = lambda rel: open(tmp_path / rel, "rb")
+    pg.transfer.verifyBackedFileHashes(eng, opener, w.backed_hashes)
+    raw = files["y.bin"].tobytes()
+    (tmp_path / "y.bin").write_bytes(bytes([raw[0] ^ 0xFF]) + raw[1:])
+    with pytest.raises(IOError, match='backed file "y.bin" content hash differs'):
+        pg.transfer.verifyBackedFileHashes(eng, opener, w.backed_hashes)

@@ -31,6 +31,9 @@ class OracleEngine:
         rec = self.chunk_digest_streams(cfg, streams, digest_set)
         return rec, np.array([oracle.xxh3_64(s) for s in streams], dtype=np.uint64)
 
+    def xxh3_batch(self, buf, off, length):
+        return np.array([oracle.xxh3_64(np.asarray(buf[int(o): int(o + l)])) for o, l in zip(off, length)], dtype=np.uint64)
+
     def digest_set(self, hint=0):
         class S:
             def __init__(s): s.s = oracle.DigestSet()
@@ -97,3 +100,24 @@ def test_batching_threshold_flushes_and_previous_index_seeds_the_known_set():
     idx = w.Finish()
     assert eng.calls == 2
     assert all(r.known for r in idx if r.path == "same") and not any(r.known for r in idx if r.path == "new")
+
+
+def test_verify_backed_file_hashes_mirrors_the_reference_errors(tmp_path):
+    """verifyBackedFileHashes (commit.go:957-976): unchanged files pass, a changed file and a missing file fail with
+    the reference's messages; several files share one batched hash call."""
+    eng = OracleEngine()
+    files = {"a/x.bin": rnd(70_000, 11), "b.bin": rnd(10, 12), "empty": rnd(0, 13), "big": rnd(300_000, 14)}
+    for k, v in files.items():
+        (tmp_path / k).parent.mkdir(parents=True, exist_ok=True)
+        (tmp_path / k).write_bytes(v.tobytes())
+    hashes = {k: oracle.xxh3_64(v) for k, v in files.items()}
+    opener = lambda rel: open(tmp_path / rel, "rb")
+    transfer.verifyBackedFileHashes(eng, opener, hashes)                       # all unchanged
+    transfer.verifyBackedFileHashes(eng, opener, hashes, batch_bytes=50_000)   # split over several batches
+    (tmp_path / "b.bin").write_bytes(b"changed!!!")
+    with pytest.raises(IOError, match='backed file "b.bin" content hash differs'):
+        transfer.verifyBackedFileHashes(eng, opener, hashes)
+    (tmp_path / "b.bin").write_bytes(files["b.bin"].tobytes())
+    (tmp_path / "big").unlink()
+    with pytest.raises(IOError, match='open backed file "big" for verification'):
+        transfer.verifyBackedFileHashes(eng, opener, hashes)
