@@ -96,6 +96,15 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def instr_ceiling(sm_count, sm_mhz, achieved_gbs):
+    """Integer-pipe bound of SHA-256 on this GPU: 64 ALU thread-ops / clk / SM over 21.9 instructions per byte."""
+    if not sm_mhz:
+        return None
+    gbs = sm_count * 64 * float(sm_mhz) * 1e6 / (1400.0 / 64.0) / 1e9
+    return {"alu_pipe_GBps": gbs, "frac_of_alu_pipe": achieved_gbs / gbs if gbs else None,
+            "saturated_kernel_GBps_measured": 810.0, "source": "profiles/r01_sha_saturated_modes.txt, r01_microbench.txt"}
+
+
 def union_ms(intervals):
     """Total length of the union of [t0,t1] intervals (ms)."""
     tot, cur0, cur1 = 0.0, None, None
@@ -305,6 +314,10 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "how": "algorithmic bytes (1 per input byte) of all K launches / union of the launches' CUDA-event "
                    "intervals on their launching streams (launches of consecutive steps overlap)",
             "scan_kernel": {"achieved": scan_gbs, "frac": scan_gbs / peak},
+            # why the dominant kernel sits far below the HBM line: SHA-256 costs ~1400 integer instructions per 64 B
+            # block (21.9 per byte, the count of the straightforward formulation: 14 per round + 10 per schedule word)
+            # and B200 retires 64 integer-ALU thread-instructions per clock per SM (profiles/r01_microbench.txt)
+            "instruction_ceiling": instr_ceiling(info["sm_count"], clocks.get("sm_mhz"), sha_gbs),
             "isolated_step_ms": {k: t_iso[k] for k in ("scan_ms", "sort_ms", "resolve_ms", "sha_ms", "sha_long_ms",
                                                         "sha_bulk_ms", "total_ms")},
         },
