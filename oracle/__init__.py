@@ -98,6 +98,11 @@ def lib():
         L.orc_xxh3_64.argtypes = [C.c_void_p, C.c_uint64]
         L.orc_xxh3_64.restype = C.c_uint64
         L.orc_corpus_fill_mt.argtypes = [C.POINTER(Corpus), C.c_uint64, C.c_void_p, C.c_uint32, C.c_uint32]
+        L.orc_chunk_digest_forced.argtypes = [C.POINTER(Cfg), C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
+                                              C.c_void_p, C.c_uint64]
+        L.orc_chunk_digest_forced.restype = C.c_uint64
+        L.orc_corpus_chunk_digest_mt.argtypes = [C.POINTER(Cfg), C.POINTER(Corpus), C.c_uint64, C.c_uint32, C.c_uint32,
+                                                 C.c_void_p, C.c_uint64, C.c_void_p]
         _lib = L
     return _lib
 
@@ -192,6 +197,30 @@ def chunk_digest_streams(cfg: Cfg, streams, threads: int = 1) -> np.ndarray:
                                    n_out.ctypes.data)
     assert rc == 0
     return np.concatenate([out[i * cap: i * cap + int(n_out[i])] for i in range(n)])
+
+
+def chunk_digest_forced(cfg: Cfg, data, forced, stream: int = 0) -> np.ndarray:
+    """One stream with suggested boundaries (strictly increasing offsets), see orc_chunk_digest_forced."""
+    a = _buf(data)
+    f = np.ascontiguousarray(forced, dtype=np.uint64)
+    cap = len(a) // cfg.min + len(f) + 2
+    out = np.zeros(cap, dtype=CHUNK_DTYPE)
+    n = lib().orc_chunk_digest_forced(C.byref(cfg), stream, a.ctypes.data, len(a), f.ctypes.data, len(f),
+                                      out.ctypes.data, cap)
+    assert n <= cap
+    return out[:n].copy()
+
+
+def corpus_chunk_digest(cfg: Cfg, c: Corpus, first_file: int, n_files: int, threads: int | None = None) -> np.ndarray:
+    """Chunk records of whole corpus files, generated on the fly per worker (no 64 GiB host copy)."""
+    threads = threads or os.cpu_count() or 1
+    cap = c.file_len // cfg.min + 2
+    out = np.zeros(n_files * cap, dtype=CHUNK_DTYPE)
+    n_out = np.zeros(n_files, dtype=np.uint64)
+    rc = lib().orc_corpus_chunk_digest_mt(C.byref(cfg), C.byref(c), first_file, n_files, threads, out.ctypes.data, cap,
+                                          n_out.ctypes.data)
+    assert rc == 0, rc
+    return np.concatenate([out[i * cap: i * cap + int(n_out[i])] for i in range(n_files)])
 
 
 class DigestSet:

@@ -352,6 +352,43 @@ uint64_t orc_chunk_digest(const orc_cfg *cfg, uint32_t stream, const uint8_t *da
 }
 
 /* ------------------------------------------------------------------------- */
+/* a2 caveat: SUGGESTED BOUNDARIES.  Newer upstream PBS wraps the chunker of
+ * the archive PAYLOAD stream in a `PayloadChunker` (pbs-datastore/src/chunker.rs) that may also cut
+ * at "suggested boundaries" = the offsets at which a file's PAYLOAD header starts in the ppxar
+ * stream (what the reference's writer produces per file at commit.go:720 / pxarfs.go:408-411).
+ * Upstream's rule, per chunk starting at `base`: a pending boundary B is dropped when
+ * B - base < min; when min <= B - base <= max the chunk is cut AT B unless the hash test cuts
+ * earlier; when B - base > max the plain chunker decides and B stays pending.  (Upstream's outcome
+ * additionally depends on how many unscanned bytes its async reader happens to hold when B becomes
+ * known; restated here in the limit of byte-wise arrival, the only timing-independent reading.)
+ * Whether pbs-plus/pxar v0.19.2 does this is UNVERIFIED -- it is an optional input everywhere.
+ * forced[] must be strictly increasing stream offsets in (0, len). */
+uint64_t orc_chunk_digest_forced(const orc_cfg *cfg, uint32_t stream, const uint8_t *data, uint64_t len,
+                                 const uint64_t *forced, uint64_t n_forced, orc_chunk *out, uint64_t cap) {
+    orc_chunker c;
+    orc_chunker_reset(&c);
+    uint64_t n = 0, base = 0, fi = 0;
+    while (base < len) {
+        while (fi < n_forced && (forced[fi] <= base || forced[fi] - base < cfg->min)) fi++;   /* past or too small: ignored */
+        uint64_t limit = len;            /* bytes the plain chunker may look at for this chunk */
+        int at_boundary = 0;
+        if (fi < n_forced && forced[fi] < len && forced[fi] - base <= cfg->max) { limit = forced[fi]; at_boundary = 1; }
+        uint64_t r = orc_chunker_scan(cfg, &c, data + base, limit - base);
+        uint64_t end;
+        if (r) { end = base + r; if (at_boundary && end == limit) fi++; }
+        else if (at_boundary) { end = limit; orc_chunker_reset(&c); fi++; }
+        else end = len;
+        if (n < cap) {
+            out[n].stream = stream; out[n].flags = 0; out[n].end_off = end;
+            orc_sha256(data + base, end - base, out[n].digest);
+        }
+        n++;
+        base = end;
+    }
+    return n;
+}
+
+/* ------------------------------------------------------------------------- */
 /* a4: known-digest set (open addressing, exact 32-byte compare)              */
 /* ------------------------------------------------------------------------- */
 typedef struct {
@@ -542,6 +579,38 @@ int orc_corpus_fill_mt(const orc_corpus *c, uint64_t first_file, uint8_t *const 
         if (pthread_create(&th[t], NULL, fill_worker, &j)) return -11;
     for (uint32_t t = 0; t < threads; t++) pthread_join(th[t], NULL);
     return 0;
+}
+
+/* Whole corpus files without materialising the corpus: every worker generates one file at a time into its
+ * own buffer and chunks + digests it (the full-size cfg2 / cfg5 parity checks: 1024 x 64 MiB would
+ * otherwise need 64 GiB of host memory).  out: n_files * cap_per_file records, n_out per file. */
+typedef struct {
+    const orc_cfg *cfg; const orc_corpus *c; uint64_t first_file; uint32_t n;
+    orc_chunk *out; uint64_t cap; uint64_t *n_out; volatile uint32_t next; volatile int oom;
+} cgen_job;
+static void *cgen_worker(void *arg) {
+    cgen_job *j = (cgen_job *)arg;
+    uint8_t *buf = (uint8_t *)malloc(j->c->file_len ? j->c->file_len : 1);
+    if (!buf) { j->oom = 1; return NULL; }
+    for (;;) {
+        uint32_t i = __atomic_fetch_add(&j->next, 1, __ATOMIC_RELAXED);
+        if (i >= j->n) break;
+        orc_corpus_fill(j->c, j->first_file + i, 0, buf, j->c->file_len);
+        j->n_out[i] = orc_chunk_digest(j->cfg, i, buf, j->c->file_len, j->out + (uint64_t)i * j->cap, j->cap);
+    }
+    free(buf);
+    return NULL;
+}
+int orc_corpus_chunk_digest_mt(const orc_cfg *cfg, const orc_corpus *c, uint64_t first_file, uint32_t n_files,
+                               uint32_t threads, orc_chunk *out, uint64_t cap_per_file, uint64_t *n_out) {
+    cgen_job j = {cfg, c, first_file, n_files, out, cap_per_file, n_out, 0, 0};
+    if (threads < 1) threads = 1;
+    if (threads > 256) threads = 256;
+    pthread_t th[256];
+    for (uint32_t t = 0; t < threads; t++)
+        if (pthread_create(&th[t], NULL, cgen_worker, &j)) return -11;
+    for (uint32_t t = 0; t < threads; t++) pthread_join(th[t], NULL);
+    return j.oom ? -12 : 0;
 }
 
 /* ====================================================================================================

@@ -195,6 +195,80 @@ def test_golden_vectors():
         assert hashlib.sha256(data.tobytes()).hexdigest() == g["data_sha256"]
 
 
+def test_go_golden_vectors_pin_the_oracle():
+    """tests/golden/gen_golden.go emits chunks_go.jsonl from the REAL Go module (github.com/pbs-plus/pxar v0.19.2,
+    reference go.mod:28, call site commit.go:302-305).  When a maintainer commits that file this test pins -- or
+    refutes -- the restated oracle cut for cut and digest for digest; until then boundary parity stays UNPINNED."""
+    path = GOLDEN / "chunks_go.jsonl"
+    if not path.exists():
+        pytest.skip("parity unpinned: no Go toolchain / module here; run tests/golden/gen_golden.go and commit chunks_go.jsonl")
+    n = 0
+    for ln in path.read_text().splitlines():
+        g = json.loads(ln)
+        c = oracle.corpus(seed=g["seed"], file_len=g["len"], block_len=g["block_len"])
+        data = oracle.corpus_file(c, g["file_id"])
+        assert hashlib.sha256(data.tobytes()).hexdigest() == g["data_sha256"], "corpus recipe differs"
+        rec = oracle.chunk_digest(oracle.config(g["avg"]), data)
+        assert rec["end_off"].tolist() == g["cuts"], (g["seed"], g["avg"], g["oracle"])
+        assert [bytes(x).hex() for x in rec["digest"]] == g["digests"]
+        n += 1
+    assert n >= 5
+    tab = GOLDEN / "table_go.json"            # optional: {"sha256_le_u32": "..."} printed from the module's table
+    if tab.exists():
+        want = json.loads((GOLDEN / "table_fingerprint.json").read_text())["sha256_le_u32"]
+        assert json.loads(tab.read_text())["sha256_le_u32"] == want
+
+
+def test_go_harness_uses_the_same_cases_as_the_oracle_goldens():
+    """The Go program and make_golden.py must describe the same inputs (the 256-byte-average case cannot be expressed
+    in KiB and is oracle-only)."""
+    go = (GOLDEN / "gen_golden.go").read_text()
+    assert "github.com/pbs-plus/pxar/buzhash" in go and "buzhash.NewConfig(" in go
+    recs = [json.loads(l) for l in (GOLDEN / "chunks_oracle.jsonl").read_text().splitlines()]
+    for g in recs:
+        if g["avg"] < 1024:
+            continue
+        assert (g["seed"], g["file_id"], g["len"], g["avg"], g["block_len"]) in _go_cases(go)
+
+
+def _go_cases(go_src):
+    import re
+    vals = set()
+    for tup in re.findall(r"\{([0-9<+ ,]+)\}", go_src):
+        parts = [re.sub(r"(\d+)\s*<<\s*(\d+)", r"(\1<<\2)", x) for x in tup.split(",")]   # Go: << binds tighter than +
+        if len(parts) == 5:
+            vals.add(tuple(int(eval(x)) for x in parts))
+    return vals
+
+
+def test_suggested_boundaries_rule():
+    """SURVEY.md 8 a2 caveat: optional suggested boundaries (file starts in the payload stream).  No boundaries = the
+    plain chunker; a boundary is taken iff it lies in [min, max] of the running chunk and no hash cut comes first;
+    every chunk but the last stays within [min, max]."""
+    cfg = oracle.config(4096)
+    rng = np.random.default_rng(7)
+    data = rng.integers(0, 256, 1 << 20, dtype=np.uint8)
+    plain = oracle.chunk_digest(cfg, data)
+    assert (oracle.chunk_digest_forced(cfg, data, []) == plain).all()
+    forced = np.sort(rng.choice(np.arange(1, len(data)), 64, replace=False)).astype(np.uint64)
+    rec = oracle.chunk_digest_forced(cfg, data, forced)
+    ends = rec["end_off"].astype(np.int64)
+    starts = np.concatenate([[0], ends[:-1]])
+    L = ends - starts
+    assert (L[:-1] >= cfg.min).all() and (L <= cfg.max).all() and ends[-1] == len(data)
+    taken = np.isin(ends, forced)
+    assert taken.sum() > 10
+    for s, e, d in zip(starts, ends, rec["digest"]):
+        assert bytes(d) == hashlib.sha256(data[s:e].tobytes()).digest()
+        # the chunk [s, e) is what the plain chunker would cut from s, truncated at the first eligible boundary
+        f = forced[(forced >= s + cfg.min) & (forced <= s + cfg.max)]
+        lim = int(f[0]) if len(f) else len(data)
+        p = oracle.chunk_ends(cfg, data[s:lim])
+        assert e == s + (int(p[0]) if len(p) else lim - s)
+    # boundaries at every hash cut change nothing
+    assert (oracle.chunk_digest_forced(cfg, data, plain["end_off"][:-1]) == plain).all()
+
+
 def test_xxh3_64_is_pinned_against_libxxhash():
     """Row f2 (commit.go:717-725): the oracle's XXH3-64 restatement equals the independent python-xxhash binding
     for every length class (0, 1-3, 4-8, 9-16, 17-128, 129-240, > 240 with and without full blocks) and for
