@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PBSGPU_VERSION 100 /* 0.1.0 */
+#define PBSGPU_VERSION 200 /* 0.2.0 */
 
 /* error codes (negative errno values) */
 #define PBSGPU_OK 0
@@ -125,11 +125,42 @@ int pbsgpu_chunk_digest_batch(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg, const void
 /* Asynchronous form for DEVICE-resident input: submit returns as soon as the
  * kernels are enqueued; several jobs may be in flight (they overlap on the GPU,
  * which hides the sequential tail of the longest chunk's SHA-256).  wait blocks,
- * copies the chunks out and frees the job.  `set` must be NULL here (probe order
- * across overlapping jobs would be undefined); probe after wait. */
+ * copies the chunks out and frees the job -- except on PBSGPU_ERANGE, where the job stays
+ * valid: call wait again with the capacity reported in *n_out, or pbsgpu_batch_free.
+ * (A digest set can be attached with pbsgpu_batch_submit_ex.) */
 int pbsgpu_batch_submit(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg, const void *base_dev, const uint64_t *off,
                         const uint64_t *len, uint32_t n, pbsgpu_job **job);
 int pbsgpu_batch_wait(pbsgpu_job *job, pbsgpu_chunk *out, uint64_t cap, uint64_t *n_out, pbsgpu_timing *timing);
+
+/* Extended batch form: everything the calls above take, plus
+ *  - SUGGESTED BOUNDARIES (SURVEY.md section 8 a2 caveat): offsets at which the caller would like a cut -- the
+ *    starts of the files' PAYLOAD headers when the stream is a pxar v2 payload stream (the bytes the production
+ *    chunker sees: 16-byte PAYLOAD header + content per file, concatenated; internal/pxarmount/pxarfs.go:408-411,
+ *    writer calls commit.go:720,:858).  Rule (upstream PBS `PayloadChunker`, restated for byte-wise arrival): with
+ *    the running chunk starting at `base`, a boundary B with B - base < min is dropped; with min <= B - base <= max
+ *    the chunk ends at B unless the hash test cuts earlier; with B - base > max the plain chunker decides and B
+ *    stays pending.  Pairs (forced_stream[i], forced_off[i]) sorted by (stream, offset), offsets in (0, len);
+ *    needs cfg->min >= 65 (avg >= 512).  Whether pbs-plus/pxar v0.19.2 applies such boundaries is UNVERIFIED;
+ *    n_forced = 0 gives the plain chunker.
+ *  - a digest set for the asynchronous form too: the probe + insert runs as kernels on the job's stream
+ *    (jobs that share a set are ordered in submission order), flags come back with the records.
+ *  - stream_xxh3[n] (may be NULL): as pbsgpu_chunk_digest_batch_xxh3 (synchronous form only).
+ * `size` must be sizeof(pbsgpu_batch_opts) (forward compatibility). */
+typedef struct pbsgpu_batch_opts {
+    uint32_t size, flags;
+    pbsgpu_set *set;
+    const uint32_t *forced_stream;
+    const uint64_t *forced_off;
+    uint64_t n_forced;
+    uint64_t *stream_xxh3;
+} pbsgpu_batch_opts;
+int pbsgpu_chunk_digest_batch_ex(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg, const void *base, const uint64_t *off,
+                                 const uint64_t *len, uint32_t n, const pbsgpu_batch_opts *opts, pbsgpu_chunk *out,
+                                 uint64_t cap, uint64_t *n_out);
+int pbsgpu_batch_submit_ex(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg, const void *base_dev, const uint64_t *off,
+                           const uint64_t *len, uint32_t n, const pbsgpu_batch_opts *opts, pbsgpu_job **job);
+/* Frees a job without collecting it (after a failed wait, or to abandon it); waits for its kernels. */
+void pbsgpu_batch_free(pbsgpu_job *job);
 
 /* Boundary scan only (a2): chunk END offsets per stream, no digests.
  * ends: caller array of cap u64; stream_first[i]..stream_first[i+1] index it
@@ -153,6 +184,18 @@ int pbsgpu_stream_write(pbsgpu_stream *s, const void *host_data, uint64_t len);
 int pbsgpu_stream_poll(pbsgpu_stream *s, pbsgpu_chunk *out, uint64_t cap, uint64_t *n_out);
 int pbsgpu_stream_finish(pbsgpu_stream *s);
 void pbsgpu_stream_close(pbsgpu_stream *s);
+/* Zero-copy staging for the streaming form: reserve hands out up to pbsgpu_stream_slot_bytes() of PINNED memory owned
+ * by the stream (a ring of 8 slots); the caller reads its io.Reader straight into it and commits the byte count, which
+ * starts the DMA and returns at once.  reserve blocks only while every slot still waits for its DMA.  write() is
+ * reserve + memcpy + commit for pageable memory and a direct DMA for pinned caller memory. */
+int pbsgpu_stream_reserve(pbsgpu_stream *s, void **buf);
+int pbsgpu_stream_commit(pbsgpu_stream *s, uint64_t len);
+uint64_t pbsgpu_stream_slot_bytes(const pbsgpu_stream *s);
+/* Suggested boundary at absolute stream offset `offset` (>= bytes written so far, strictly increasing): what the
+ * payload-stream writer calls right before it writes a file's PAYLOAD header.  Rule as in pbsgpu_batch_opts. */
+int pbsgpu_stream_suggest(pbsgpu_stream *s, uint64_t offset);
+/* Bytes written so far (= the payload offset the next entry will get in the mpxar PAYLOAD_REF). */
+uint64_t pbsgpu_stream_position(const pbsgpu_stream *s);
 
 /* ---- a4: known-digest set -------------------------------------------------------
  * Replaces the known-chunk bookkeeping of the reference's dedup session:
@@ -170,6 +213,20 @@ int pbsgpu_set_count(pbsgpu_set *set, uint64_t *count);
 /* Seed from a PBS dynamic index (.didx) image: 4096-byte header + 40-byte
  * {u64 end_le, digest[32]} entries (what origPayloadIdx holds, commit.go:324-329). */
 int pbsgpu_set_seed_didx(pbsgpu_set *set, const uint8_t *didx, uint64_t size, uint64_t *n_entries);
+
+/* ---- e: multi-GPU merge of the digest set (SURVEY.md section 8 e / 8 b) -----------------------------------------
+ * One process (or thread) per GPU chunks its own shard of the files; the ONE exchange step is an NCCL all-gather of
+ * every rank's new digests over NVLink, after which every rank inserts ALL gathered digests into its replica of the
+ * set in global (rank, index) order.  hit[i] (HOST, n bytes, may be NULL) = this rank's digest i was known before the
+ * call or occurs earlier in that global order -- so with files sharded in rank order the flags equal a single-GPU run.
+ * Collective: every rank of the communicator must call it, in the same order.  d32 HOST or DEVICE, n may be 0.
+ * `nccl_comm` is an ncclComm_t the caller owns (libnccl.so.2 is resolved with dlopen at first use; PBSGPU_NCCL_LIB
+ * overrides the path); the three helpers below create one for callers without an NCCL binding of their own
+ * (the 128-byte unique id travels by whatever channel the ranks share). */
+int pbsgpu_set_allgather(pbsgpu_set *set, void *nccl_comm, const uint8_t *d32, uint64_t n, uint8_t *hit);
+int pbsgpu_nccl_unique_id(uint8_t id[128]);
+int pbsgpu_nccl_comm_create(pbsgpu_ctx *ctx, const uint8_t id[128], int nranks, int rank, void **comm);
+void pbsgpu_nccl_comm_destroy(void *comm);
 
 /* ---- f1 ("next" row of SURVEY.md section 8): PBS dynamic index (.didx) images ----------------
  * The (end offset, digest) list of a finished archive lands in `<name>.mpxar.didx` /
@@ -195,6 +252,12 @@ int pbsgpu_didx_parse(pbsgpu_ctx *ctx, const uint8_t *didx, uint64_t size, uint6
 int pbsgpu_crc32_batch(pbsgpu_ctx *ctx, const void *base, const uint64_t *off, const uint64_t *len, uint32_t n,
                        uint32_t *crc_out);
 void pbsgpu_blob_header(uint32_t crc, uint8_t out[12]);
+/* Complete uncompressed DataBlobs { magic[8], crc32 LE, payload } of n byte ranges (the NEW chunks of a batch) in one
+ * call: blob i is written to out + out_off[i] (HOST memory, 12 + len[i] bytes; pbsgpu_blob_size gives that), the CRCs
+ * come from K6, payload bytes are copied from `base` (HOST or DEVICE).  crc_out (may be NULL) also receives the CRCs. */
+uint64_t pbsgpu_blob_size(uint64_t payload_len);
+int pbsgpu_blob_encode_batch(pbsgpu_ctx *ctx, const void *base, const uint64_t *off, const uint64_t *len, uint32_t n,
+                             uint8_t *out, const uint64_t *out_off, uint32_t *crc_out);
 
 /* ---- f2 ("next" row): the commit walk's per-file content hash ----------------------------------
  * emitBackedFile tees every new file through `xxh3.New()` and keeps `h.Sum64()` (reference

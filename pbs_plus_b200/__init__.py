@@ -5,8 +5,8 @@ known-digest probe.  The product is libpbsgpu.so (csrc/, C ABI in include/pbsgpu
 this package is the Python host mirror used by tests and bench.py.
 """
 from ._lib import CHUNK_DTYPE, CHUNK_KNOWN, LIB_PATH, PbsGpuError  # noqa: F401
-from .engine import DigestSet, Engine, Job, Stream, corpus, default_table, make_config  # noqa: F401
+from .engine import DigestSet, Engine, Job, NcclComm, Stream, corpus, default_table, make_config  # noqa: F401
 from . import buzhash, transfer  # noqa: F401
 
-__all__ = ["Engine", "DigestSet", "Job", "Stream", "make_config", "default_table", "corpus", "buzhash", "transfer",
+__all__ = ["Engine", "DigestSet", "Job", "Stream", "NcclComm", "make_config", "default_table", "corpus", "buzhash", "transfer",
            "CHUNK_DTYPE", "CHUNK_KNOWN", "PbsGpuError", "LIB_PATH"]

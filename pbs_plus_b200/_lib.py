@@ -54,6 +54,12 @@ class Timing(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class BatchOpts(C.Structure):
+    """pbsgpu_batch_opts: digest set, suggested boundaries, per-stream XXH3 output."""
+    _fields_ = [("size", C.c_uint32), ("flags", C.c_uint32), ("set", C.c_void_p), ("forced_stream", C.c_void_p),
+                ("forced_off", C.c_void_p), ("n_forced", C.c_uint64), ("stream_xxh3", C.c_void_p)]
+
+
 class Corpus(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("file_len", C.c_uint64), ("block_len", C.c_uint64),
                 ("run_blocks", C.c_uint32), ("dup_permille", C.c_uint32), ("edit_mode", C.c_uint32),
@@ -65,10 +71,14 @@ SYMBOLS = [
     "pbsgpu_version", "pbsgpu_open", "pbsgpu_close", "pbsgpu_strerror", "pbsgpu_device_info",
     "pbsgpu_set_profiling", "pbsgpu_partition_info", "pbsgpu_set_kernel_variant", "pbsgpu_config", "pbsgpu_config_kib",
     "pbsgpu_default_table", "pbsgpu_chunk_digest_batch", "pbsgpu_batch_submit", "pbsgpu_batch_wait",
+    "pbsgpu_chunk_digest_batch_ex", "pbsgpu_batch_submit_ex", "pbsgpu_batch_free",
     "pbsgpu_scan_batch", "pbsgpu_sha256_batch", "pbsgpu_stream_open", "pbsgpu_stream_write",
-    "pbsgpu_stream_poll", "pbsgpu_stream_finish", "pbsgpu_stream_close", "pbsgpu_set_create",
+    "pbsgpu_stream_poll", "pbsgpu_stream_finish", "pbsgpu_stream_close", "pbsgpu_stream_reserve", "pbsgpu_stream_commit",
+    "pbsgpu_stream_slot_bytes", "pbsgpu_stream_suggest", "pbsgpu_stream_position", "pbsgpu_set_create",
     "pbsgpu_set_destroy", "pbsgpu_set_insert", "pbsgpu_set_probe", "pbsgpu_set_count", "pbsgpu_set_seed_didx",
+    "pbsgpu_set_allgather", "pbsgpu_nccl_unique_id", "pbsgpu_nccl_comm_create", "pbsgpu_nccl_comm_destroy",
     "pbsgpu_didx_size", "pbsgpu_didx_build", "pbsgpu_didx_parse", "pbsgpu_crc32_batch", "pbsgpu_blob_header",
+    "pbsgpu_blob_size", "pbsgpu_blob_encode_batch",
     "pbsgpu_xxh3_batch", "pbsgpu_chunk_digest_batch_xxh3",
     "pbsgpu_host_alloc", "pbsgpu_host_free", "pbsgpu_corpus_fill",
 ]
@@ -103,6 +113,10 @@ def lib() -> C.CDLL:
     L.pbsgpu_chunk_digest_batch.argtypes = [vp, C.POINTER(Cfg), vp, vp, vp, C.c_uint32, vp, vp, C.c_uint64, u64p]
     L.pbsgpu_batch_submit.argtypes = [vp, C.POINTER(Cfg), vp, vp, vp, C.c_uint32, C.POINTER(vp)]
     L.pbsgpu_batch_wait.argtypes = [vp, vp, C.c_uint64, u64p, C.POINTER(Timing)]
+    L.pbsgpu_chunk_digest_batch_ex.argtypes = [vp, C.POINTER(Cfg), vp, vp, vp, C.c_uint32, C.POINTER(BatchOpts), vp, C.c_uint64, u64p]
+    L.pbsgpu_batch_submit_ex.argtypes = [vp, C.POINTER(Cfg), vp, vp, vp, C.c_uint32, C.POINTER(BatchOpts), C.POINTER(vp)]
+    L.pbsgpu_batch_free.argtypes = [vp]
+    L.pbsgpu_batch_free.restype = None
     L.pbsgpu_scan_batch.argtypes = [vp, C.POINTER(Cfg), vp, vp, vp, C.c_uint32, vp, C.c_uint64, vp, u64p]
     L.pbsgpu_sha256_batch.argtypes = [vp, vp, vp, vp, C.c_uint32, vp]
     L.pbsgpu_stream_open.argtypes = [vp, C.POINTER(Cfg), vp, C.POINTER(vp)]
@@ -111,6 +125,21 @@ def lib() -> C.CDLL:
     L.pbsgpu_stream_finish.argtypes = [vp]
     L.pbsgpu_stream_close.argtypes = [vp]
     L.pbsgpu_stream_close.restype = None
+    L.pbsgpu_stream_reserve.argtypes = [vp, C.POINTER(vp)]
+    L.pbsgpu_stream_commit.argtypes = [vp, C.c_uint64]
+    L.pbsgpu_stream_slot_bytes.argtypes = [vp]
+    L.pbsgpu_stream_slot_bytes.restype = C.c_uint64
+    L.pbsgpu_stream_suggest.argtypes = [vp, C.c_uint64]
+    L.pbsgpu_stream_position.argtypes = [vp]
+    L.pbsgpu_stream_position.restype = C.c_uint64
+    L.pbsgpu_set_allgather.argtypes = [vp, vp, vp, C.c_uint64, vp]
+    L.pbsgpu_nccl_unique_id.argtypes = [vp]
+    L.pbsgpu_nccl_comm_create.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(vp)]
+    L.pbsgpu_nccl_comm_destroy.argtypes = [vp]
+    L.pbsgpu_nccl_comm_destroy.restype = None
+    L.pbsgpu_blob_size.argtypes = [C.c_uint64]
+    L.pbsgpu_blob_size.restype = C.c_uint64
+    L.pbsgpu_blob_encode_batch.argtypes = [vp, vp, vp, vp, C.c_uint32, vp, vp, vp]
     L.pbsgpu_set_create.argtypes = [vp, C.c_uint64, C.POINTER(vp)]
     L.pbsgpu_set_destroy.argtypes = [vp]
     L.pbsgpu_set_destroy.restype = None

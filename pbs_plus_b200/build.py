@@ -16,7 +16,8 @@ HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 OBJ = HERE / "_obj"
 LIB = HERE / "libpbsgpu.so"
-SOURCES = ["scan.cu", "resolve.cu", "sha256.cu", "digestset.cu", "crc32.cu", "xxh3.cu", "corpus.cu", "capi.cu"]
+SOURCES = ["scan.cu", "resolve.cu", "sha256.cu", "digestset.cu", "crc32.cu", "xxh3.cu", "corpus.cu", "capi.cu", "capi_set.cu",
+           "capi_stream.cu", "capi_aux.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -25,7 +26,7 @@ FLAGS = [
 
 
 def _deps(src: Path) -> float:
-    hdrs = list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.inc")) + [HERE.parent / "include" / "pbsgpu.h"]
+    hdrs = list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.hpp")) + list(CSRC.glob("*.inc")) + [HERE.parent / "include" / "pbsgpu.h"]
     return max([src.stat().st_mtime] + [h.stat().st_mtime for h in hdrs])
 
 
@@ -50,7 +51,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     objs = [str(OBJ / (n + ".o")) for n in SOURCES]
     if jobs or not LIB.exists():
         run([NVCC, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a",
-             "-Xcompiler", "-fPIC", "-o", str(LIB), *objs])
+             "-Xcompiler", "-fPIC", "-o", str(LIB), *objs, "-ldl"])
     return LIB
 
 

@@ -67,6 +67,8 @@ struct ResolveArgs {
     unsigned long long *n_chunks;          // device total
 };
 cudaError_t launch_resolve(const ResolveArgs &a, cudaStream_t st);   // count + scan + write (3 launches)
+cudaError_t launch_append_keys(const uint64_t *keys, uint64_t n, uint64_t *cand, uint64_t cand_cap, unsigned long long *cand_count,
+                               cudaStream_t st);
 
 // ---- SHA-256 (K3) ----------------------------------------------------------------
 struct ShaArgs {
@@ -82,13 +84,20 @@ struct ShaArgs {
     const unsigned long long *n_head;    // device; NULL with part 0
     int part;                            // 0 = everything, 1 = head only, 2 = everything but the head
 };
+// per-context tuning knobs of K3 (read from the environment once per pbsgpu_open)
+struct ShaTune {
+    int mode = 2;        // PBSGPU_SHA_MODE: instruction mix of the throughput kernel (0,1,2,3,7) or split-only (10..13)
+    int hybrid = 1;      // PBSGPU_SHA_HYBRID: 0 throughput kernel only, 1 hybrid when partitioned, 2 hybrid always
+    int thr_x10 = 25;    // PBSGPU_HYBRID_THR_X10: chunks longer than thr_x10/10 x avg take the latency kernel
+    int serial = 0;      // PBSGPU_HYBRID_SERIAL: latency kernel on the job's own stream (diagnostic)
+    int spread_kb = 30;  // PBSGPU_SPLIT_SPREAD_KB: dummy dynamic shared memory per latency CTA (caps CTAs per SM)
+};
 cudaError_t launch_sha_simple(const ShaArgs &a, cudaStream_t st);
-cudaError_t launch_sha_tuned(const ShaArgs &a, int sm_count, cudaStream_t st);   // throughput kernel
-cudaError_t launch_sha_split(const ShaArgs &a, cudaStream_t st);                 // latency kernel
+cudaError_t launch_sha_tuned(const ShaArgs &a, const ShaTune &tune, cudaStream_t st);   // throughput kernel
+cudaError_t launch_sha_split(const ShaArgs &a, const ShaTune &tune, cudaStream_t st);   // latency kernel
 cudaError_t launch_split_point(const uint32_t *len_sorted_desc, const unsigned long long *n_chunks, uint64_t cap,
                                uint32_t threshold, unsigned long long max_head, unsigned long long *n_head,
                                cudaStream_t st);
-int sha_hybrid_enabled();
 cudaError_t launch_len_keys(const ChunkRef *chunks, const unsigned long long *n_chunks, uint64_t cap,
                             uint32_t *keys, uint32_t *vals, cudaStream_t st);
 cudaError_t launch_pack_chunks(const ChunkRef *chunks, const uint8_t *digests, const uint8_t *hit,
@@ -105,6 +114,17 @@ cudaError_t launch_set_mark_probe_insert(SetTable t, const uint8_t *d32, const u
                                          const uint32_t *idx_sorted, uint64_t n, int do_insert, uint8_t *hit,
                                          uint8_t *is_rep_miss, unsigned long long *n_new, cudaStream_t st);
 cudaError_t launch_set_rehash(SetTable from, SetTable to, cudaStream_t st);
+// fused form (K4 on a job's stream): the element count lives on the device, `cap` bounds the launch; nothing happens when
+// *guard > guard_max.  Padding entries (index >= *n_dev) get the all-ones tag and sort last.
+cudaError_t launch_set_make_keys_dev(const uint8_t *d32, const unsigned long long *n_dev, uint64_t cap, uint64_t *tag, uint32_t *idx,
+                                     cudaStream_t st);
+cudaError_t launch_set_mark_probe_insert_dev(SetTable t, const uint8_t *d32, const uint64_t *tag_sorted, const uint32_t *idx_sorted,
+                                             const unsigned long long *n_dev, uint64_t cap, const unsigned long long *guard,
+                                             uint64_t guard_max, uint8_t *hit, uint8_t *is_rep_miss, unsigned long long *n_new,
+                                             cudaStream_t st);
+// multi-GPU merge: compact the padded all-gather payload [rank][max_n][32] into global order [sum(counts)][32]
+cudaError_t launch_set_compact_gather(const uint8_t *padded, const uint64_t *counts_dev, uint32_t nranks, uint64_t max_n,
+                                      uint8_t *dense, cudaStream_t st);
 
 // ---- CRC-32 (K6, DataBlob checksums) -----------------------------------------------------
 cudaError_t launch_crc32(const uint8_t *base, const uint64_t *off, const uint64_t *len, const uint64_t *wb_first,

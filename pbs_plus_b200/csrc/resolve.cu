@@ -92,6 +92,23 @@ __global__ void __launch_bounds__(1024) k_scan_counts(const uint32_t *counts, ui
     if (threadIdx.x == 0) { first[n] = carry; *total = carry; }
 }
 
+// Suggested boundaries (pbsgpu_batch_opts.forced_*): appended to the candidate list as ordinary keys "cut after byte
+// B-1 of stream s"; the min/max rule above then treats them exactly like hash candidates, which is upstream's
+// PayloadChunker rule for byte-wise arrival (a boundary closer than min to the chunk start is skipped, one within
+// [min, max] cuts unless a hash candidate comes first, one beyond max waits for the next chunk).
+__global__ void k_append_keys(const uint64_t *keys, uint64_t n, uint64_t *cand, uint64_t cand_cap, unsigned long long *cand_count) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long slot = atomicAdd(cand_count, 1ull);
+    if (slot < cand_cap) cand[slot] = keys[i];
+}
+cudaError_t launch_append_keys(const uint64_t *keys, uint64_t n, uint64_t *cand, uint64_t cand_cap, unsigned long long *cand_count,
+                               cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    k_append_keys<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(keys, n, cand, cand_cap, cand_count);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_resolve(const ResolveArgs &a, cudaStream_t st) {
     if (a.n_streams == 0) return cudaMemsetAsync(a.n_chunks, 0, sizeof(unsigned long long), st);
     unsigned blocks = (a.n_streams + 127) / 128;

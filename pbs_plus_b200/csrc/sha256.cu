@@ -12,7 +12,6 @@
 // ops per byte), not HBM bound -- see DESIGN.md for the ceiling this implies.
 #include <cuda_runtime.h>
 #include <stdint.h>
-#include <stdlib.h>
 
 #include "internal.cuh"
 
@@ -407,27 +406,15 @@ __global__ void __launch_bounds__(64) k_sha_split(ShaArgs a, Opq o) {
     }
 }
 
-static int g_sha_mode = -1, g_sha_hybrid = -1;
-static void sha_env() {
-    if (g_sha_mode < 0) {
-        const char *e = getenv("PBSGPU_SHA_MODE");
-        g_sha_mode = e ? atoi(e) : 2;
-        const char *h = getenv("PBSGPU_SHA_HYBRID");
-        g_sha_hybrid = h ? atoi(h) : 1;
-    }
-}
-int sha_hybrid_enabled() { sha_env(); return g_sha_hybrid && g_sha_mode < 10; }
-
 // throughput kernel (mode 0: the compiler's own pipe choice; 2: + schedule shifts on the FMA pipe;
-// 1/3/7: more aggressive offloads, measured slower -- issue-rate bound)
-cudaError_t launch_sha_tuned(const ShaArgs &a, int sm_count, cudaStream_t st) {
-    (void)sm_count;
+// 1/3/7: more aggressive offloads -- see DESIGN.md and tools/sha_lab.cu).  `mode` comes from the context
+// (PBSGPU_SHA_MODE read once per pbsgpu_open), never from process-wide state.
+cudaError_t launch_sha_tuned(const ShaArgs &a, const ShaTune &tune, cudaStream_t st) {
     if (a.chunk_cap == 0) return cudaSuccess;
-    sha_env();
-    if (g_sha_mode >= 10 && a.part == 0) return launch_sha_split(a, st);
+    if (tune.mode >= 10 && a.part == 0) return launch_sha_split(a, tune, st);
     Opq o{1u, 1u << 29, 1u << 22, 1u << 7};
     unsigned blocks = (unsigned)((a.chunk_cap + 31) / 32);
-    switch (g_sha_mode) {
+    switch (tune.mode) {
         case 0: k_sha_tuned<0><<<blocks, 32, 0, st>>>(a, o); break;
         case 1: k_sha_tuned<1><<<blocks, 32, 0, st>>>(a, o); break;
         case 3: k_sha_tuned<3><<<blocks, 32, 0, st>>>(a, o); break;
@@ -440,32 +427,29 @@ cudaError_t launch_sha_tuned(const ShaArgs &a, int sm_count, cudaStream_t st) {
 // latency kernel (producer/consumer warps).
 // When it is launched next to a kernel that already occupies every SM, the CTA scheduler packs its
 // few CTAs onto a handful of SMs (measured: 4x slower than on an empty GPU).  In the hybrid launch
-// (part 1) each CTA therefore also asks for more than half an SM's shared memory, which caps it at
-// ONE CTA per SM and forces the spread; the throughput kernel uses no shared memory and still
-// co-resides.
+// (part 1) each CTA therefore also asks for `spread_kb` KiB of dummy dynamic shared memory, which caps the
+// CTAs per SM (30 -> 4, 85 -> 2, 112 -> 1) and forces the spread; the throughput kernel uses no shared
+// memory and still co-resides.
 template <int PM, int CM>
-static cudaError_t launch_split_t(const ShaArgs &a, const Opq &o, unsigned blocks, cudaStream_t st) {
+static cudaError_t launch_split_t(const ShaArgs &a, const Opq &o, unsigned blocks, int spread_kb, cudaStream_t st) {
     size_t dyn = 0;
-    static int spread = -1;   // KiB of dummy dynamic shared memory per CTA (0 = off); 112 -> 1 CTA/SM, 85 -> 2
-    if (spread < 0) { const char *e = getenv("PBSGPU_SPLIT_SPREAD_KB"); spread = e ? atoi(e) : 30; }   // 30 KiB -> 4 CTAs/SM
-    if (a.part == 1 && spread) {
-        dyn = (size_t)spread * 1024;
+    if (a.part == 1 && spread_kb > 0) {
+        dyn = (size_t)spread_kb * 1024;
         cudaError_t e = cudaFuncSetAttribute(k_sha_split<PM, CM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
         if (e != cudaSuccess) return e;
     }
     k_sha_split<PM, CM><<<blocks, 64, dyn, st>>>(a, o);
     return cudaGetLastError();
 }
-cudaError_t launch_sha_split(const ShaArgs &a, cudaStream_t st) {
+cudaError_t launch_sha_split(const ShaArgs &a, const ShaTune &tune, cudaStream_t st) {
     if (a.chunk_cap == 0) return cudaSuccess;
-    sha_env();
     Opq o{1u, 1u << 29, 1u << 22, 1u << 7};
     unsigned blocks = (unsigned)((a.chunk_cap + 31) / 32);
-    switch (g_sha_mode) {
-        case 10: return launch_split_t<0, 0>(a, o, blocks, st);
-        case 12: return launch_split_t<0, 1>(a, o, blocks, st);
-        case 13: return launch_split_t<3, 1>(a, o, blocks, st);
-        default: return launch_split_t<3, 0>(a, o, blocks, st);   // producer balanced, consumer IADD3
+    switch (tune.mode) {
+        case 10: return launch_split_t<0, 0>(a, o, blocks, tune.spread_kb, st);
+        case 12: return launch_split_t<0, 1>(a, o, blocks, tune.spread_kb, st);
+        case 13: return launch_split_t<3, 1>(a, o, blocks, tune.spread_kb, st);
+        default: return launch_split_t<3, 0>(a, o, blocks, tune.spread_kb, st);   // producer balanced, consumer IADD3
     }
 }
 

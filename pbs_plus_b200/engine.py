@@ -13,7 +13,7 @@ from typing import Iterable, Sequence
 import numpy as np
 
 from . import _lib
-from ._lib import CHUNK_DTYPE, CHUNK_KNOWN, Cfg, Corpus, DevInfo, PbsGpuError, Timing
+from ._lib import CHUNK_DTYPE, CHUNK_KNOWN, BatchOpts, Cfg, Corpus, DevInfo, PbsGpuError, Timing
 
 
 def _ptr(x) -> int:
@@ -117,17 +117,38 @@ class Engine:
         m = max(int(cfg.min), 65)
         return int((l // np.uint64(m)).sum()) + len(l) + 1
 
-    def chunk_digest_batch(self, cfg: Cfg, base, off, length, digest_set: "DigestSet | None" = None) -> np.ndarray:
+    @staticmethod
+    def _opts(digest_set, forced, xxh3=None):
+        """pbsgpu_batch_opts; `forced` = (stream u32[], offset u64[]) suggested boundaries sorted by (stream, offset)."""
+        o = BatchOpts()
+        o.size = C.sizeof(BatchOpts)
+        o.set = digest_set._h if digest_set is not None else None
+        keep = []
+        if forced is not None:
+            fs = np.ascontiguousarray(forced[0], dtype=np.uint32)
+            fo = np.ascontiguousarray(forced[1], dtype=np.uint64)
+            if fs.shape != fo.shape or fs.ndim != 1:
+                raise ValueError("forced = (stream[], offset[]) of equal length")
+            o.forced_stream, o.forced_off, o.n_forced = fs.ctypes.data, fo.ctypes.data, len(fs)
+            keep += [fs, fo]
+        if xxh3 is not None:
+            o.stream_xxh3 = xxh3.ctypes.data
+        return o, keep
+
+    def chunk_digest_batch(self, cfg: Cfg, base, off, length, digest_set: "DigestSet | None" = None,
+                           forced=None) -> np.ndarray:
         """stream -> chunks -> digests for n streams; `base` device (tensor/int) or host (numpy).
-        Replaces n calls of writer.WriteEntryReader (reference commit.go:720)."""
+        Replaces n calls of writer.WriteEntryReader (reference commit.go:720).  `forced` = optional suggested
+        boundaries (stream[], offset[]): file starts of a pxar payload stream (pxarfs.go:408-411)."""
         o, l = self._offlen(off, length)
-        cap = self._chunk_cap(cfg, l)
+        cap = self._chunk_cap(cfg, l) + (len(forced[0]) if forced is not None else 0)
         out = np.zeros(cap, dtype=CHUNK_DTYPE)
         n_out = C.c_uint64()
         keep = base  # keep the buffer alive for the duration of the call
-        self._ck(self._L.pbsgpu_chunk_digest_batch(
-            self._h, C.byref(cfg), _ptr(keep), o.ctypes.data, l.ctypes.data, len(o),
-            digest_set._h if digest_set is not None else None, out.ctypes.data, cap, C.byref(n_out)))
+        opts, _k = self._opts(digest_set, forced)
+        self._ck(self._L.pbsgpu_chunk_digest_batch_ex(
+            self._h, C.byref(cfg), _ptr(keep), o.ctypes.data, l.ctypes.data, len(o), C.byref(opts), out.ctypes.data, cap,
+            C.byref(n_out)))
         return out[: n_out.value]
 
     def chunk_digest_batch_xxh3(self, cfg: Cfg, base, off, length, digest_set: "DigestSet | None" = None):
@@ -158,12 +179,15 @@ class Engine:
             buf[int(o): int(o) + len(a)] = a
         return self.chunk_digest_batch(cfg, buf, offs, lens, digest_set)
 
-    def submit(self, cfg: Cfg, base_dev, off, length) -> "Job":
+    def submit(self, cfg: Cfg, base_dev, off, length, digest_set: "DigestSet | None" = None, forced=None) -> "Job":
+        """Asynchronous form; with `digest_set` the probe + insert runs as kernels on the job's stream (jobs sharing a
+        set are ordered in submission order) and the KNOWN flags come back with the records."""
         o, l = self._offlen(off, length)
         h = C.c_void_p()
-        self._ck(self._L.pbsgpu_batch_submit(self._h, C.byref(cfg), _ptr(base_dev), o.ctypes.data, l.ctypes.data,
-                                             len(o), C.byref(h)))
-        return Job(self, h, self._chunk_cap(cfg, l), base_dev)
+        opts, _k = self._opts(digest_set, forced)
+        self._ck(self._L.pbsgpu_batch_submit_ex(self._h, C.byref(cfg), _ptr(base_dev), o.ctypes.data, l.ctypes.data,
+                                                len(o), C.byref(opts), C.byref(h)))
+        return Job(self, h, self._chunk_cap(cfg, l) + (len(forced[0]) if forced is not None else 0), base_dev)
 
     def scan_batch(self, cfg: Cfg, base_dev, off, length):
         """Boundaries only (a2).  Returns (ends, stream_first)."""
@@ -199,6 +223,18 @@ class Engine:
         out = np.zeros(len(o), dtype=np.uint32)
         self._ck(self._L.pbsgpu_crc32_batch(self._h, _ptr(base), o.ctypes.data, l.ctypes.data, len(o), out.ctypes.data))
         return out
+
+    def blob_encode_batch(self, base, off, length):
+        """Complete uncompressed DataBlobs (magic | crc32 | payload) of n ranges -> (bytes buffer, blob_off[n+1], crc[n])."""
+        o, l = self._offlen(off, length)
+        sizes = l + np.uint64(12)
+        boff = np.zeros(len(o) + 1, dtype=np.uint64)
+        np.cumsum(sizes, out=boff[1:])
+        out = np.zeros(int(boff[-1]), dtype=np.uint8)
+        crc = np.zeros(len(o), dtype=np.uint32)
+        self._ck(self._L.pbsgpu_blob_encode_batch(self._h, _ptr(base), o.ctypes.data, l.ctypes.data, len(o),
+                                                  out.ctypes.data if len(out) else None, boff.ctypes.data, crc.ctypes.data))
+        return out, boff, crc
 
     def blob_header(self, crc: int) -> bytes:
         out = np.zeros(12, dtype=np.uint8)
@@ -269,10 +305,22 @@ class Job:
         out = np.zeros(self._cap, dtype=CHUNK_DTYPE)
         n_out = C.c_uint64()
         t = Timing()
-        h, self._h = self._h, None
-        self._eng._ck(self._eng._L.pbsgpu_batch_wait(h, out.ctypes.data, self._cap, C.byref(n_out), C.byref(t)))
+        h = self._h
+        rc = self._eng._L.pbsgpu_batch_wait(h, out.ctypes.data, self._cap, C.byref(n_out), C.byref(t))
+        if rc == _lib.ERANGE:                       # the job stays valid: retry with the reported capacity
+            self._cap = int(n_out.value)
+            out = np.zeros(self._cap, dtype=CHUNK_DTYPE)
+            rc = self._eng._L.pbsgpu_batch_wait(h, out.ctypes.data, self._cap, C.byref(n_out), C.byref(t))
+        self._h = None
+        self._eng._ck(rc)
         self._keep = None
         return out[: n_out.value], t.as_dict()
+
+    def free(self):
+        """Abandon the job (pbsgpu_batch_free)."""
+        if self._h is not None:
+            self._eng._L.pbsgpu_batch_free(self._h)
+            self._h, self._keep = None, None
 
 
 class DigestSet:
@@ -313,11 +361,47 @@ class DigestSet:
     def probe(self, digests) -> np.ndarray:
         return self._run(self._eng._L.pbsgpu_set_probe, digests)
 
+    def allgather(self, comm: "NcclComm", digests) -> np.ndarray:
+        """The ONE multi-GPU exchange step (pbsgpu_set_allgather): every rank contributes its digests, every replica
+        inserts all of them in global (rank, index) order; returns this rank's flags."""
+        d = np.ascontiguousarray(digests, dtype=np.uint8).reshape(-1, 32)
+        hit = np.zeros(len(d), dtype=np.uint8)
+        self._eng._ck(self._eng._L.pbsgpu_set_allgather(self._h, comm._h, d.ctypes.data if len(d) else None, len(d),
+                                                         hit.ctypes.data if len(d) else None))
+        return hit
+
     def seed_didx(self, image: bytes) -> int:
         a = np.frombuffer(image, dtype=np.uint8)
         n = C.c_uint64()
         self._eng._ck(self._eng._L.pbsgpu_set_seed_didx(self._h, a.ctypes.data, len(a), C.byref(n)))
         return int(n.value)
+
+
+class NcclComm:
+    """An ncclComm_t created through the C ABI's helpers (no torch): rank 0 makes the unique id, every rank passes
+    the same 128 bytes (distributed by whatever channel the ranks share) to pbsgpu_nccl_comm_create."""
+
+    def __init__(self, eng: Engine, unique_id: bytes, nranks: int, rank: int):
+        self._eng = eng
+        ida = np.frombuffer(bytes(unique_id), dtype=np.uint8)
+        if len(ida) != 128:
+            raise ValueError("NCCL unique id is 128 bytes")
+        h = C.c_void_p()
+        eng._ck(eng._L.pbsgpu_nccl_comm_create(eng._h, ida.ctypes.data, nranks, rank, C.byref(h)))
+        self._h = h
+
+    @staticmethod
+    def unique_id() -> bytes:
+        out = np.zeros(128, dtype=np.uint8)
+        rc = _lib.lib().pbsgpu_nccl_unique_id(out.ctypes.data)
+        if rc:
+            raise PbsGpuError(rc, "NCCL unavailable (libnccl.so.2 not loadable; set PBSGPU_NCCL_LIB)")
+        return out.tobytes()
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._eng._L.pbsgpu_nccl_comm_destroy(self._h)
+            self._h = None
 
 
 class Stream:
@@ -332,6 +416,24 @@ class Stream:
     def write(self, data):
         a = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data)
         self._eng._ck(self._eng._L.pbsgpu_stream_write(self._h, a.ctypes.data if len(a) else None, len(a)))
+
+    def suggest(self, offset: int):
+        """Suggested boundary (a file's PAYLOAD header starts here) -- pbsgpu_stream_suggest."""
+        self._eng._ck(self._eng._L.pbsgpu_stream_suggest(self._h, int(offset)))
+
+    @property
+    def position(self) -> int:
+        return int(self._eng._L.pbsgpu_stream_position(self._h))
+
+    def reserve(self) -> np.ndarray:
+        """A pinned staging slot owned by the stream; fill a prefix and call commit(n)."""
+        p = C.c_void_p()
+        self._eng._ck(self._eng._L.pbsgpu_stream_reserve(self._h, C.byref(p)))
+        n = int(self._eng._L.pbsgpu_stream_slot_bytes(self._h))
+        return np.ctypeslib.as_array((C.c_uint8 * n).from_address(p.value))
+
+    def commit(self, n: int):
+        self._eng._ck(self._eng._L.pbsgpu_stream_commit(self._h, int(n)))
 
     def poll(self, cap: int = 4096) -> np.ndarray:
         out = np.zeros(cap, dtype=CHUNK_DTYPE)

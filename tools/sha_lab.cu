@@ -7,7 +7,8 @@
 // digest against variant 0 (which is checked against a host SHA-256).  `tools/sass_mix.py` counts the loop's SASS
 // per pipe for the same variants.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -o tools/sha_lab.bin tools/sha_lab.cu
-//   ./tools/sha_lab.bin [range_kib=256] [total_gib=16] [only_variant=-1]
+//   ./tools/sha_lab.bin mix [range_kib=256] [total_gib=16] [only_variant=-1]   instruction mixes at saturation
+//   ./tools/sha_lab.bin load [chain_kib=1024]                                  chain latency and GB/s vs number of concurrent chains
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -15,17 +16,11 @@
 #include <string.h>
 #include <vector>
 
-#define CK(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { printf("CUDA error %s at line %d\n", cudaGetErrorString(e__), __LINE__); exit(1); } } while (0)
+#include "../pbs_plus_b200/csrc/sha256.cu"   // product kernels (k_sha_tuned<M>, k_sha_split<P,C>) for side-by-side timing
+using pbsgpu::ChunkRef;
+using pbsgpu::ShaArgs;
 
-#define K256_LIST                                                                                          \
-    0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5,        \
-    0xd807aa98, 0x12835b01, 0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174,        \
-    0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da,        \
-    0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967,        \
-    0x27b70a85, 0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85,        \
-    0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070,        \
-    0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3,        \
-    0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2
+#define CK(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { printf("CUDA error %s at line %d\n", cudaGetErrorString(e__), __LINE__); exit(1); } } while (0)
 
 struct Opq { uint32_t one, p29, p22; };
 
@@ -177,76 +172,142 @@ static void host_sha256(const uint8_t *msg, size_t len, uint8_t out[32]) {
     for (int i = 0; i < 8; i++) { out[4 * i] = h[i] >> 24; out[4 * i + 1] = h[i] >> 16; out[4 * i + 2] = h[i] >> 8; out[4 * i + 3] = h[i]; }
 }
 
-struct Variant { const char *name; void (*launch)(const uint8_t *, const uint64_t *, const uint64_t *, uint32_t, uint8_t *, Opq); };
-template <int V, int THREADS, int MINB>
-static void launch(const uint8_t *base, const uint64_t *off, const uint64_t *len, uint32_t n, uint8_t *dig, Opq o) {
-    k_lab<V, THREADS, MINB><<<(n + THREADS - 1) / THREADS, THREADS>>>(base, off, len, n, dig, o);
+struct Work {
+    const uint8_t *buf; const uint64_t *off, *len; uint32_t n; uint8_t *dig;
+    const ChunkRef *refs; const unsigned long long *n_dev;   // product-kernel view of the same ranges
+};
+struct Variant { const char *name; void (*launch)(const Work &); };
+
+template <int V, int THREADS, int MINB> static void lab(const Work &w) {
+    Opq o{1u, 1u << 29, 1u << 22};
+    k_lab<V, THREADS, MINB><<<(w.n + THREADS - 1) / THREADS, THREADS>>>(w.buf, w.off, w.len, w.n, w.dig, o);
+}
+static ShaArgs sha_args(const Work &w) {
+    ShaArgs a; a.base = w.buf; a.off = nullptr; a.chunks = w.refs; a.order = nullptr; a.n_chunks = w.n_dev; a.chunk_cap = w.n;
+    a.digests = w.dig; a.n_head = nullptr; a.part = 0; return a;
+}
+template <int M> static void prod_tuned(const Work &w) {
+    pbsgpu::Opq o{1u, 1u << 29, 1u << 22, 1u << 7};
+    pbsgpu::k_sha_tuned<M><<<(w.n + 31) / 32, 32>>>(sha_args(w), o);
+}
+template <int P, int C> static void prod_split(const Work &w) {
+    pbsgpu::Opq o{1u, 1u << 29, 1u << 22, 1u << 7};
+    pbsgpu::k_sha_split<P, C><<<(w.n + 31) / 32, 64>>>(sha_args(w), o);
 }
 
-int main(int argc, char **argv) {
-    const uint64_t rk = argc > 1 ? atoll(argv[1]) : 256, tg = argc > 2 ? atoll(argv[2]) : 16;
-    const int only = argc > 3 ? atoi(argv[3]) : -1;
-    const uint64_t total = tg << 30, R = rk << 10;
-    const uint32_t n = (uint32_t)(total / R);
-    cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
-    printf("device %s, %d SMs; %u ranges x %llu KiB (misaligned by 3)\n", prop.name, prop.multiProcessorCount, n, (unsigned long long)rk);
-    uint8_t *buf, *dig, *dig0; uint64_t *d_off, *d_len;
-    CK(cudaMalloc(&buf, total + 256)); CK(cudaMalloc(&dig, (size_t)n * 32)); CK(cudaMalloc(&dig0, (size_t)n * 32));
-    CK(cudaMalloc(&d_off, n * 8)); CK(cudaMalloc(&d_len, n * 8));
-    k_fill<<<4096, 256>>>((uint64_t *)buf, total / 8, 77); CK(cudaDeviceSynchronize());
-    std::vector<uint64_t> off(n), len(n);
-    for (uint32_t i = 0; i < n; i++) { off[i] = (uint64_t)i * R + 3; len[i] = R - 64 + 5; }
-    CK(cudaMemcpy(d_off, off.data(), n * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(d_len, len.data(), n * 8, cudaMemcpyHostToDevice));
-    const Variant vs[] = {
-        {"v0  plain C (ptxas decides)                 32 thr", launch<0, 32, 1>},
-        {"v3  sched adds + K+W on FMA                 32 thr", launch<3, 32, 1>},
-        {"v7  v3 + off-critical round adds on FMA     32 thr", launch<7, 32, 1>},
-        {"v11 ALL adds on FMA (T shared)              32 thr", launch<11, 32, 1>},
-        {"v23 v7 + sched shifts as IMAD.HI            32 thr", launch<23, 32, 1>},
-        {"v27 v11 + sched shifts as IMAD.HI           32 thr", launch<27, 32, 1>},
-        {"v16 only sched shifts as IMAD.HI (mode 2)   32 thr", launch<16, 32, 1>},
-        {"v0                                          64 thr", launch<0, 64, 1>},
-        {"v11                                         64 thr", launch<11, 64, 1>},
-        {"v7                                          64 thr", launch<7, 64, 1>},
-        {"v0                                         128 thr", launch<0, 128, 1>},
-        {"v11                                        128 thr", launch<11, 128, 1>},
-        {"v7                                         128 thr", launch<7, 128, 1>},
-        {"v11 regs<=64 (128 thr x 8 blocks)          128 thr", launch<11, 128, 8>},
-        {"v7  regs<=64 (128 thr x 8 blocks)          128 thr", launch<7, 128, 8>},
-        {"v0  regs<=64 (128 thr x 8 blocks)          128 thr", launch<0, 128, 8>},
-        {"v11 regs<=80 (128 thr x 6 blocks)          128 thr", launch<11, 128, 6>},
-        {"v27 regs<=80 (128 thr x 6 blocks)          128 thr", launch<27, 128, 6>},
-    };
-    const int nv = (int)(sizeof vs / sizeof vs[0]);
-    Opq o{1u, 1u << 29, 1u << 22};
-    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    std::vector<uint8_t> h0((size_t)n * 32), h1((size_t)n * 32);
-    for (int v = 0; v < nv; v++) {
-        if (only >= 0 && v != only && v != 0) continue;
-        uint8_t *out = v == 0 ? dig0 : dig;
-        CK(cudaMemset(out, 0, (size_t)n * 32));
-        vs[v].launch(buf, d_off, d_len, n, out, o); CK(cudaGetLastError()); CK(cudaDeviceSynchronize());
+static const Variant VS[] = {
+    {"v0   plain C (ptxas decides)         32 thr, <=72 regs", lab<0, 32, 28>},
+    {"v3   sched adds + K+W on FMA         32 thr, <=72 regs", lab<3, 32, 28>},
+    {"v7   v3 + off-critical round adds    32 thr, <=72 regs", lab<7, 32, 28>},
+    {"v11  ALL adds on FMA                 32 thr, <=72 regs", lab<11, 32, 28>},
+    {"v27  v11 + sched shifts IMAD.HI      32 thr, <=72 regs", lab<27, 32, 28>},
+    {"v16  sched shifts IMAD.HI (= mode 2) 32 thr, <=72 regs", lab<16, 32, 28>},
+    {"v0                                   32 thr, <=64 regs", lab<0, 32, 32>},
+    {"v11                                  32 thr, <=64 regs", lab<11, 32, 32>},
+    {"v27                                  32 thr, <=64 regs", lab<27, 32, 32>},
+    {"v0                                   32 thr, <=96 regs", lab<0, 32, 21>},
+    {"v11                                  32 thr, <=96 regs", lab<11, 32, 21>},
+    {"v0                                  128 thr, <=72 regs", lab<0, 128, 7>},
+    {"v11                                 128 thr, <=72 regs", lab<11, 128, 7>},
+    {"v27                                 128 thr, <=72 regs", lab<27, 128, 7>},
+    {"v11                                 128 thr, <=64 regs", lab<11, 128, 8>},
+    {"v27                                 128 thr, <=64 regs", lab<27, 128, 8>},
+    {"v11                                 256 thr, <=64 regs", lab<11, 256, 4>},
+    {"product k_sha_tuned<2>", prod_tuned<2>},
+    {"product k_sha_tuned<3>", prod_tuned<3>},
+    {"product k_sha_split<3,0>", prod_split<3, 0>},
+    {"product k_sha_split<3,1>", prod_split<3, 1>},
+};
+static const int NV = (int)(sizeof VS / sizeof VS[0]);
+
+struct Bench {
+    uint8_t *buf = nullptr, *dig = nullptr, *dig0 = nullptr; uint64_t *d_off = nullptr, *d_len = nullptr; ChunkRef *d_refs = nullptr;
+    unsigned long long *d_n = nullptr; uint64_t total = 0; uint32_t cap_n = 0;
+    cudaEvent_t e0, e1;
+    void init(uint64_t total_bytes, uint32_t max_n) {
+        total = total_bytes; cap_n = max_n;
+        CK(cudaMalloc(&buf, total + 4096)); CK(cudaMalloc(&dig, (size_t)max_n * 32)); CK(cudaMalloc(&dig0, (size_t)max_n * 32));
+        CK(cudaMalloc(&d_off, (size_t)max_n * 8)); CK(cudaMalloc(&d_len, (size_t)max_n * 8)); CK(cudaMalloc(&d_refs, (size_t)max_n * sizeof(ChunkRef)));
+        CK(cudaMalloc(&d_n, 8));
+        k_fill<<<4096, 256>>>((uint64_t *)buf, (total + 4096) / 8, 77); CK(cudaDeviceSynchronize());
+        CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    }
+    // n equal ranges of `len` bytes at stride `stride`, misaligned by 3
+    Work setup(uint32_t n, uint64_t stride, uint64_t len, std::vector<uint64_t> &off, std::vector<uint64_t> &ln) {
+        off.resize(n); ln.resize(n); std::vector<ChunkRef> refs(n);
+        for (uint32_t i = 0; i < n; i++) { off[i] = (uint64_t)i * stride + 3; ln[i] = len; refs[i].stream = 0; refs[i].len = (uint32_t)len; refs[i].start = off[i]; }
+        unsigned long long hn = n;
+        CK(cudaMemcpy(d_off, off.data(), (size_t)n * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(d_len, ln.data(), (size_t)n * 8, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(d_refs, refs.data(), (size_t)n * sizeof(ChunkRef), cudaMemcpyHostToDevice)); CK(cudaMemcpy(d_n, &hn, 8, cudaMemcpyHostToDevice));
+        return Work{buf, d_off, d_len, n, dig, d_refs, d_n};
+    }
+    float time(const Variant &v, Work w, int reps) {
+        CK(cudaMemset(w.dig, 0, (size_t)w.n * 32));
+        v.launch(w); CK(cudaGetLastError()); CK(cudaDeviceSynchronize());
         float best = 1e9f;
-        for (int rep = 0; rep < 3; rep++) {
-            CK(cudaEventRecord(e0));
-            vs[v].launch(buf, d_off, d_len, n, out, o);
-            CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+        for (int r = 0; r < reps; r++) {
+            CK(cudaEventRecord(e0)); v.launch(w); CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
             float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); if (ms < best) best = ms;
         }
-        bool ok = true;
-        if (v == 0) {
-            CK(cudaMemcpy(h0.data(), dig0, (size_t)n * 32, cudaMemcpyDeviceToHost));
-            std::vector<uint8_t> m(len[5]); uint8_t ref[32];
-            CK(cudaMemcpy(m.data(), buf + off[5], len[5], cudaMemcpyDeviceToHost));
-            host_sha256(m.data(), m.size(), ref);
-            ok = memcmp(ref, &h0[5 * 32], 32) == 0;
-        } else {
-            CK(cudaMemcpy(h1.data(), dig, (size_t)n * 32, cudaMemcpyDeviceToHost));
-            ok = memcmp(h0.data(), h1.data(), (size_t)n * 32) == 0;
+        return best;
+    }
+};
+
+int main(int argc, char **argv) {
+    const char *mode = argc > 1 ? argv[1] : "mix";
+    cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
+    const int sms = prop.multiProcessorCount;
+    printf("device %s, %d SMs, mode %s\n", prop.name, sms, mode);
+    Bench B;
+    std::vector<uint64_t> off, ln;
+    if (!strcmp(mode, "mix")) {
+        // saturation: every SM sub-partition has as many warps as the launch shape allows, equal ranges
+        const uint64_t rk = argc > 2 ? atoll(argv[2]) : 256, tg = argc > 3 ? atoll(argv[3]) : 16;
+        const int only = argc > 4 ? atoi(argv[4]) : -1;
+        const uint64_t R = rk << 10; const uint32_t n = (uint32_t)((tg << 30) / R);
+        B.init(tg << 30, n);
+        Work w = B.setup(n, R, R - 64 + 5, off, ln);
+        printf("%u ranges x %llu KiB\n", n, (unsigned long long)rk);
+        std::vector<uint8_t> h0((size_t)n * 32), h1((size_t)n * 32);
+        for (int v = 0; v < NV; v++) {
+            if (only >= 0 && v != only && v != 0) continue;
+            Work wv = w; if (v == 0) wv.dig = B.dig0;
+            const float ms = B.time(VS[v], wv, 3);
+            bool ok;
+            if (v == 0) {
+                CK(cudaMemcpy(h0.data(), B.dig0, (size_t)n * 32, cudaMemcpyDeviceToHost));
+                std::vector<uint8_t> m(ln[5]); uint8_t ref[32];
+                CK(cudaMemcpy(m.data(), B.buf + off[5], ln[5], cudaMemcpyDeviceToHost));
+                host_sha256(m.data(), m.size(), ref);
+                ok = memcmp(ref, &h0[5 * 32], 32) == 0;
+            } else {
+                CK(cudaMemcpy(h1.data(), B.dig, (size_t)n * 32, cudaMemcpyDeviceToHost));
+                ok = memcmp(h0.data(), h1.data(), (size_t)n * 32) == 0;
+            }
+            printf("[%2d] %-56s %8.2f ms  %7.1f GB/s  %s\n", v, VS[v].name, ms, (double)n * ln[0] / ms / 1e6, ok ? "ok" : "MISMATCH");
+            fflush(stdout);
         }
-        const double bytes = (double)n * (double)len[0];
-        printf("[%2d] %-52s %8.2f ms  %7.1f GB/s  %s\n", v, vs[v].name, best, bytes / best / 1e6, ok ? "ok" : "MISMATCH");
-        fflush(stdout);
+    } else if (!strcmp(mode, "load")) {
+        // load curve: C concurrent chains of equal length; time per 64 B block of a chain = the chain latency that bounds
+        // a batch's makespan, GB/s = throughput at that load.  C = 148 SMs x 4 sub-partitions x 32 lanes x {1/4 .. 8} warps.
+        const uint64_t chain = (argc > 2 ? atoll(argv[2]) : 1024) << 10;   // bytes per chain
+        const int picks[] = {0, 3, 4, 17, 19, 20};                          // v0, v11, v27, tuned<2>, split<3,0>, split<3,1>
+        const uint32_t base_c = (uint32_t)sms * 4 * 32;
+        const double mult[] = {0.25, 0.5, 1, 2, 4, 8};
+        const uint32_t max_n = (uint32_t)(base_c * 8);
+        B.init((uint64_t)max_n * chain > (64ull << 30) ? (64ull << 30) : (uint64_t)max_n * chain, max_n);
+        printf("chains of %llu KiB; C chains = m x %u (one warp per sub-partition at m = 1)\n", (unsigned long long)(chain >> 10), base_c);
+        for (int pi = 0; pi < 6; pi++) {
+            for (int mi = 0; mi < 6; mi++) {
+                const uint32_t n = (uint32_t)(base_c * mult[mi]);
+                uint64_t len = chain; while ((uint64_t)n * len > B.total) len >>= 1;   // keep within the buffer
+                Work w = B.setup(n, len, len - 64 + 5, off, ln);
+                const float ms = B.time(VS[picks[pi]], w, 2);
+                printf("%-40.40s C=%7u (m=%4.2f) len %5llu KiB: %8.2f ms  %7.1f GB/s  %6.3f us per 64 B block of a chain\n", VS[picks[pi]].name, n,
+                       mult[mi], (unsigned long long)(len >> 10), ms, (double)n * ln[0] / ms / 1e6, ms * 1e3 / (double)(ln[0] / 64));
+                fflush(stdout);
+            }
+        }
     }
     return 0;
 }
