@@ -96,13 +96,18 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def instr_ceiling(sm_count, sm_mhz, achieved_gbs):
-    """Integer-pipe bound of SHA-256 on this GPU: 64 ALU thread-ops / clk / SM over 21.9 instructions per byte."""
+def instr_ceiling(sm_total, sm_mhz, value_gbs):
+    """Integer-pipe bound of SHA-256 on this GPU.  Every one of the chip's SMs runs SHA work (124 the bulk kernel, 24
+    the long-chunk kernel), so the bound counts ALL of them: 64 ALU-pipe thread-instructions / clk / SM
+    (profiles/r01_microbench.txt) over the ALU instructions per byte of the shipped kernel
+    (profiles/r02_sass_mix.txt: loop of k_sha_tuned<2>, 1226 ALU-pipe instructions per 64 B block)."""
     if not sm_mhz:
         return None
-    gbs = sm_count * 64 * float(sm_mhz) * 1e6 / (1400.0 / 64.0) / 1e9
-    return {"alu_pipe_GBps": gbs, "frac_of_alu_pipe": achieved_gbs / gbs if gbs else None,
-            "saturated_kernel_GBps_measured": 810.0, "source": "profiles/r01_sha_saturated_modes.txt, r01_microbench.txt"}
+    alu_per_block = 1226.0
+    gbs = sm_total * 64 * float(sm_mhz) * 1e6 / (alu_per_block / 64.0) / 1e9
+    return {"alu_pipe_GBps": gbs, "frac_of_alu_pipe": value_gbs / gbs if gbs else None, "sm_count": sm_total,
+            "alu_instr_per_64B": alu_per_block,
+            "source": "profiles/r02_sass_mix.txt (SASS count), profiles/r01_microbench.txt (64 thread-ops/clk/SM)"}
 
 
 def union_ms(intervals):
@@ -191,11 +196,109 @@ def run_reference(args, rank: int, world: int):
 
 
 # ------------------------------------------------------------------------------------------
+def cpu_legs_b1_b3():
+    """the oracle on cfg1 (one 1 GiB stream, seed 1, 4 MiB average) with ONE thread -- whole path,
+    scan only, SHA-256 only."""
+    import oracle
+
+    n = 1 << 30
+    data = oracle.corpus_file(oracle.corpus(seed=1, file_len=n), 0)
+    cfg = oracle.config(4 << 20)
+    t0 = time.perf_counter(); rec = oracle.chunk_digest(cfg, data); t_all = time.perf_counter() - t0
+    t0 = time.perf_counter(); ends = oracle.chunk_ends(cfg, data); t_scan = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    s = 0
+    for e in ends.tolist():
+        oracle.sha256(data[s:e]); s = e
+    t_sha = time.perf_counter() - t0
+    assert rec["end_off"].tolist() == ends.tolist()
+    return {"B1_chunk+sha_1thread_GiBps": n / t_all / GIB, "B3_scan_only_1thread_GiBps": n / t_scan / GIB,
+            "B3_sha_only_1thread_GiBps": n / t_sha / GIB, "input": "cfg1: one 1 GiB stream (seed 1), 4 MiB average chunk",
+            "chunks": int(len(rec)), "sha": "SHA-NI" if oracle.lib().orc_have_shani() else "portable C"}
+
+
+def h2d_roofline(torch, host_arr, nbytes=8 << 30):
+    """Measured pinned-host -> device copy bandwidth on THIS box in THIS run: the roofline of the e2e figure."""
+    n = min(len(host_arr), nbytes)
+    dst = torch.empty(n, dtype=torch.uint8, device="cuda")
+    src = torch.from_numpy(np.asarray(host_arr[:n]))
+    dst.copy_(src, non_blocking=True); torch.cuda.synchronize()
+    best = 0.0
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); dst.copy_(src, non_blocking=True); e1.record(); e1.synchronize()
+        best = max(best, n / (e0.elapsed_time(e1) / 1e3) / 1e9)
+    del dst
+    return best
+
+
+def run_distinct(args, eng, pg, torch, cfg, total_gib=768, batch_files=256, nbuf=7):
+    """value_distinct: the same path over NON-REPEATING data (the cfg3 corpus, generated on the device batch by batch):
+    every batch is hashed once, a buffer is refilled only after its job was collected.  Depth is bounded by HBM
+    (nbuf x batch), not by the number of steps -- the honest counterpart of the repeated-buffer headline."""
+    file_len = args.file_mib << 20
+    corp = pg.corpus(seed=3, file_len=file_len, block_len=4 << 20, run_blocks=8, dup_permille=300)
+    known = eng.digest_set(1 << 20)
+    bufs = [torch.empty(batch_files * file_len, dtype=torch.uint8, device="cuda") for _ in range(nbuf)]
+    off = np.arange(batch_files, dtype=np.uint64) * file_len
+    ln = np.full(batch_files, file_len, dtype=np.uint64)
+    n_batches = max(nbuf, (total_gib << 30) // (batch_files * file_len))
+    jobs = [None] * nbuf
+    chunks = hits = 0
+    gen_s = 0.0
+
+    def drain(slot):
+        nonlocal chunks, hits
+        if jobs[slot] is not None:
+            rec, _ = jobs[slot].wait()
+            chunks += len(rec); hits += int((rec["flags"] & 1).sum())
+            jobs[slot] = None
+
+    for b in range(nbuf):        # untimed: first fill + pool warm-up
+        eng.corpus_fill(corp, b * batch_files, batch_files, bufs[b], file_len)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for b in range(n_batches):
+        slot = b % nbuf
+        drain(slot)
+        if b >= nbuf:
+            g0 = time.perf_counter()
+            eng.corpus_fill(corp, b * batch_files, batch_files, bufs[slot], file_len)
+            gen_s += time.perf_counter() - g0
+        jobs[slot] = eng.submit(cfg, bufs[slot], off, ln, digest_set=known)
+    for k in range(nbuf):
+        drain((n_batches + k) % nbuf)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    nbytes = n_batches * batch_files * file_len
+    del bufs
+    torch.cuda.empty_cache()
+    return {"value": nbytes / max(1e-9, wall - gen_s) / GIB, "unit": "GiB/s", "value_incl_generation": nbytes / wall / GIB,
+            "bytes": nbytes, "batches": n_batches, "batch_GiB": batch_files * file_len / GIB, "buffers_in_flight": nbuf,
+            "chunks": chunks, "known_chunks": hits, "hit_rate": hits / max(1, chunks), "seconds": wall, "generation_s": gen_s,
+            "workload": "cfg3 corpus (seed 3, 30 % duplicate 4 MiB blocks in runs of 8), every byte hashed once; "
+                        "generation (device kernel, serialised with the submissions) excluded from `value`"}
+
+
+def expected_cfg4_hits(world, n_files, file_mib):
+    """Known-chunk count of the first pass over the global cfg4 corpus, from a ONE-set run (profiles/r02_cfg4_expected.json,
+    produced by `bench.py --workload cfg4verify`)."""
+    p = ROOT / "profiles" / "r02_cfg4_expected.json"
+    if not p.exists():
+        return None
+    try:
+        for e in json.loads(p.read_text())["entries"]:
+            if e["world"] == world and e["files_per_rank"] == n_files and e["file_mib"] == file_mib:
+                return e
+    except Exception:
+        return None
+    return None
+
+
 def run_ours(args, rank: int, local_rank: int, world: int):
     import torch
 
     import pbs_plus_b200 as pg
-    from pbs_plus_b200 import dist as pdist
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product has no CPU path (use --impl reference)")
@@ -203,9 +306,10 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     dev_t = torch.device("cuda", local_rank)
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev_t)
+        dist.init_process_group("nccl", device_id=dev_t)     # plumbing only: barrier, max over ranks, id broadcast
     eng = pg.Engine(local_rank, profiling=True)
     info = eng.device_info()
+    sm_total = torch.cuda.get_device_properties(local_rank).multi_processor_count
     file_len = args.file_mib << 20
     n_files = args.files
     budget = info["free_mem"] - (6 << 30)
@@ -213,35 +317,71 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         n_files //= 2
     reduced = n_files != args.files
     data = torch.empty(n_files * file_len, dtype=torch.uint8, device=dev_t)
-    eng.corpus_fill(pg.corpus(seed=2, file_len=file_len), rank * n_files, n_files, data, file_len)
+    if world > 1:
+        # cfg4 (BASELINE configs[3]): ONE corpus with duplicate runs (seed 3, 30 % of the 4 MiB blocks in runs of 8),
+        # sharded by contiguous file ranges -- rank r holds files [r*n, (r+1)*n) -- so duplicate runs cross rank
+        # boundaries and only the NCCL all-gather of the digests makes the KNOWN flags equal a single-GPU run
+        corp = pg.corpus(seed=3, file_len=file_len, block_len=4 << 20, run_blocks=8, dup_permille=300)
+        wl = (f"cfg4: {world} x {n_files} x {args.file_mib} MiB files of ONE duplicate-run corpus (seed 3, 30 % dup 4 MiB blocks, "
+              f"runs of 8) sharded by file range, {args.avg_kib} KiB avg chunk, chunk+SHA-256 per rank + pbsgpu_set_allgather "
+              f"(NCCL) of the digests every step, HBM-resident")
+    else:
+        corp = pg.corpus(seed=2, file_len=file_len)
+        wl = (f"cfg2: {n_files} x {args.file_mib} MiB synthetic files per GPU (seed 2), {args.avg_kib} KiB avg "
+              f"chunk (min avg/4, max 4*avg), chunk+SHA-256+probe, HBM-resident")
+    eng.corpus_fill(corp, rank * n_files, n_files, data, file_len)
     off = np.arange(n_files, dtype=np.uint64) * file_len
     ln = np.full(n_files, file_len, dtype=np.uint64)
     cfg = pg.buzhash.NewConfig(args.avg_kib)  # default 4096: the reference's call (commit.go:303) = 4 MiB
     known = eng.digest_set(1 << 20)
+    comm = None
+    if world > 1:
+        ident = [pg.NcclComm.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ident, src=0, device=dev_t)
+        comm = pg.NcclComm(eng, ident[0], world, rank)       # the library's own communicator: the merge is C ABI, not torch
     launches = {"mine": 0}
+
+    def submit():
+        # N = 1: the probe is fused into the job (K4 on the job's stream).  N > 1: the probe needs the other ranks' digests
+        return eng.submit(cfg, data, off, ln, digest_set=known if world == 1 else None)
 
     def finish(job):
         rec, t = job.wait()
         launches["mine"] += t["scan_launches"] + t["sha_launches"] + t["other_launches"]
-        if world > 1:   # the ONE exchange step: all-gather this step's digests over NCCL/NVLink
-            allg, counts = pdist.allgather_digests(rec["digest"], device=dev_t)
-            flags = pdist.global_known_flags(known, allg, counts, rank)
+        if world > 1:   # the ONE exchange step: pbsgpu_set_allgather (counts + padded digests over NCCL/NVLink, in-order insert)
+            flags = known.allgather(comm, rec["digest"])
+            launches["mine"] += 4    # compaction + make_keys + mark/probe + insert
         else:
-            flags = known.insert(rec["digest"])
-        launches["mine"] += 3    # K4: make_keys + mark/probe + insert
+            flags = (rec["flags"] & 1).astype(np.uint8)
         return rec, t, flags
 
     # ---- warm-up (untimed): W full steps, sequential, then one pipelined burst of K steps so that the
     # library's scratch pool (device + pinned buffers, events) is populated for K jobs in flight
-    for _ in range(args.warmup):
-        finish(eng.submit(cfg, data, off, ln))
+    first_pass = None
+    for _ in range(max(1, args.warmup)):
+        r = finish(submit())
+        if first_pass is None:
+            first_pass = (len(r[0]), int(r[2].sum()))
+    check = {"chunks_first_pass": first_pass[0], "known_first_pass": first_pass[1]}
+    if world > 1:
+        tot = torch.tensor(list(first_pass), dtype=torch.int64, device=dev_t)
+        dist.all_reduce(tot)
+        check = {"chunks_first_pass": int(tot[0].item()), "known_first_pass": int(tot[1].item()), "set_size": len(known)}
+        # every replica holds the same set, and it accounts for every chunk: distinct = chunks - known
+        if check["set_size"] != check["chunks_first_pass"] - check["known_first_pass"]:
+            raise SystemExit(f"bench.py: rank {rank}: digest-set replica inconsistent: {check}")
+        exp = expected_cfg4_hits(world, n_files, args.file_mib)
+        check["expected_known_single_set"] = exp["known"] if exp else None
+        if exp and (exp["known"] != check["known_first_pass"] or exp["chunks"] != check["chunks_first_pass"]):
+            raise SystemExit(f"bench.py: cfg4 hit count differs from the single-set run: {check} vs {exp}")
+        check["hit_rate_first_pass"] = check["known_first_pass"] / max(1, check["chunks_first_pass"])
     if not args.no_prewarm:
-        for j in [eng.submit(cfg, data, off, ln) for _ in range(min(args.steps, args.inflight or args.steps))]:
+        for j in [submit() for _ in range(min(args.steps, args.inflight or args.steps))]:
             finish(j)
     # latency of ONE isolated batch (includes the serial tail of the longest chunk)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    _, t_iso, _ = finish(eng.submit(cfg, data, off, ln))
+    _, t_iso, _ = finish(submit())
     torch.cuda.synchronize()
     iso_ms = (time.perf_counter() - t0) * 1e3
 
@@ -249,7 +389,6 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     launches["mine"] = 0
     sampler = ClockSampler(local_rank)
     if world > 1:
-        import torch.distributed as dist
         dist.barrier()
     torch.cuda.synchronize()
     sampler.start()
@@ -261,7 +400,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     for _ in range(args.steps):
         if len(q) >= inflight:
             results.append(finish(q.popleft()))
-        q.append(eng.submit(cfg, data, off, ln))
+        q.append(submit())
     while q:
         results.append(finish(q.popleft()))
     if world > 1:
@@ -281,10 +420,14 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     timings = [r[1] for r in results]
     n_chunks = int(timings[0]["chunks"])
     hit_last = float((results[-1][2] != 0).mean()) if len(results[-1][2]) else 0.0
+    if hit_last != 1.0:
+        raise SystemExit(f"bench.py: rank {rank}: a re-hashed step must find every digest known, got {hit_last}")
     sha_union = union_ms([(t["sha_t0"], t["sha_t1"]) for t in timings])
     scan_union = union_ms([(t["scan_t0"], t["scan_t1"]) for t in timings])
     peak, peak_src = measured_peaks()
-    traffic, traffic_src = ncu_traffic() if (n_files == 1024 and args.file_mib == 64) else (None, None)
+    traffic = ncu_traffic() if (n_files == 1024 and args.file_mib == 64) else None
+    # the roofline line follows from the SAME clock as `value`: algorithmic bytes of one step (per GPU) / ms_per_step
+    step_gbs = step_bytes / (ms / args.steps / 1e3) / 1e9
     sha_gbs = step_bytes * args.steps / (sha_union / 1e3) / 1e9 if sha_union > 0 else 0.0
     scan_gbs = step_bytes * args.steps / (scan_union / 1e3) / 1e9 if scan_union > 0 else 0.0
 
@@ -293,35 +436,45 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8/u32", "data": "synthetic",
         "config": {
-            "workload": f"cfg2: {n_files} x {args.file_mib} MiB synthetic files per GPU (seed 2), {args.avg_kib} KiB avg "
-                        f"chunk (min avg/4, max 4*avg), chunk+SHA-256+probe, HBM-resident",
+            "workload": wl,
             "reduced_to_fit_hbm": reduced, "chunks_per_step": n_chunks, "parallelism": f"files sharded x{world}",
             "l2": "inputs (>= 64 GiB) far exceed the 126 MB L2; no flush needed",
-            "pipelining": "K steps submitted asynchronously (13 stream slots, FIFO per slot); all complete inside "
-                          "the timed region",
+            "pipelining": "K steps submitted asynchronously over the SAME resident batch (13 stream slots, FIFO per slot); all "
+                          "complete inside the timed region; see value_distinct for non-repeating data",
             "inflight": args.inflight or args.steps, "sm_partition(long,bulk)": list(eng.partition_info()),
-            "known_hit_rate_last_step": hit_last,
-            "per_step_sha_interval_ms": [[round(t["sha_t0"], 1), round(t["sha_t1"], 1)] for t in timings],
+            "known_hit_rate_last_step": hit_last, "first_pass_check": check,
         },
         "clocks": clocks,
         "gpu_launches": launches["mine"],
         "single_batch_latency_ms": iso_ms,
         "roofline": {
-            "bound": "hbm", "kernel": "k_sha256 (dominant; instruction-bound integer work, see DESIGN.md)",
-            "achieved": sha_gbs, "peak": peak, "unit": "GB/s", "frac": sha_gbs / peak, "traffic": traffic,
-            "traffic_source": traffic_src, "algorithmic_bytes_per_launch": step_bytes,
-            "peak_source": peak_src,
-            "how": "algorithmic bytes (1 per input byte) of all K launches / union of the launches' CUDA-event "
-                   "intervals on their launching streams (launches of consecutive steps overlap)",
-            "scan_kernel": {"achieved": scan_gbs, "frac": scan_gbs / peak},
-            # why the dominant kernel sits far below the HBM line: SHA-256 costs ~1400 integer instructions per 64 B
-            # block (21.9 per byte, the count of the straightforward formulation: 14 per round + 10 per schedule word)
-            # and B200 retires 64 integer-ALU thread-instructions per clock per SM (profiles/r01_microbench.txt)
-            "instruction_ceiling": instr_ceiling(info["sm_count"], clocks.get("sm_mhz"), sha_gbs),
+            "bound": "hbm", "kernel": "k_sha_tuned / k_sha_split (K3, dominant; instruction-bound integer work, see DESIGN.md)",
+            "achieved": step_gbs, "peak": peak, "unit": "GB/s", "frac": step_gbs / peak,
+            "traffic": traffic["total"] if traffic else None, "traffic_detail": traffic,
+            "algorithmic_bytes_per_launch": step_bytes, "peak_source": peak_src,
+            "how": "algorithmic bytes of one step on one GPU (1 per input byte) / ms_per_step (the driver-checkable clock: "
+                   "CUDA events around the K timed steps, max over ranks); all kernels of the step included",
+            "kernel_intervals": {
+                "what": "diagnostic: bytes of all K launches / union of their CUDA-event intervals on the launching streams",
+                "sha_GBps": sha_gbs, "scan_GBps": scan_gbs, "sha_frac": sha_gbs / peak, "scan_frac": scan_gbs / peak},
+            "instruction_ceiling": instr_ceiling(sm_total, clocks.get("sm_mhz"), step_gbs),
             "isolated_step_ms": {k: t_iso[k] for k in ("scan_ms", "sort_ms", "resolve_ms", "sha_ms", "sha_long_ms",
-                                                        "sha_bulk_ms", "total_ms")},
+                                                        "sha_bulk_ms", "set_ms", "total_ms")},
         },
     }
+    # ---- untimed post-run parity check: the record list of the LAST timed step equals the oracle's
+    last_rec = results[-1][0]
+    if world == 1 and not args.no_verify and not reduced and args.avg_kib == 4096:
+        import oracle
+        t0 = time.perf_counter()
+        ref = oracle.corpus_chunk_digest(oracle.config(4 << 20), oracle.corpus(seed=2, file_len=file_len), 0, n_files)
+        ok = (len(ref) == len(last_rec) and ref["end_off"].tobytes() == last_rec["end_off"].tobytes()
+              and ref["digest"].tobytes() == last_rec["digest"].tobytes() and ref["stream"].tobytes() == last_rec["stream"].tobytes())
+        out["verify"] = {"equal_to_oracle": bool(ok), "records": int(len(ref)), "seconds": time.perf_counter() - t0,
+                         "what": "every (stream, end offset, digest) of the last timed step vs oracle/ on the host cores (untimed)"}
+        if not ok:
+            print(json.dumps(out), flush=True)
+            raise SystemExit("bench.py: GPU records differ from the oracle")
     # "next" rows measured beside the headline (never inside its timed region): K7, the commit walk's per-file
     # XXH3-64, over the same resident files through the blocking C call.
     try:
@@ -331,17 +484,23 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         dt = time.perf_counter() - t0
         try:
             import xxhash                     # independent implementation (libxxhash), when the box has it
-            check = bool(int(hashes[0]) == xxhash.xxh3_64_intdigest(data[: file_len].cpu().numpy().tobytes()))
+            check_x = bool(int(hashes[0]) == xxhash.xxh3_64_intdigest(data[: file_len].cpu().numpy().tobytes()))
         except ImportError:
-            check = None
+            check_x = None
         out["next_rows"] = {"f2_xxh3_file_hash": {
             "GBps": step_bytes / dt / 1e9, "frac_of_hbm_peak": step_bytes / dt / 1e9 / peak, "ms": dt * 1e3,
-            "files": n_files, "file0_equals_libxxhash": check,
+            "files": n_files, "file0_equals_libxxhash": check_x,
             "how": "wall time of one pbsgpu_xxh3_batch call over the step's resident files (incl. launch + D2H of the hashes)"}}
     except Exception as ex:   # an aid next to the headline: never fails the bench line
         out["next_rows"] = {"f2_xxh3_file_hash": {"error": repr(ex)}}
     del data
     torch.cuda.empty_cache()
+    if world == 1 and not args.no_distinct:
+        try:
+            out["value_distinct"] = run_distinct(args, eng, pg, torch, cfg, total_gib=args.distinct_gib)
+        except Exception as ex:
+            out["value_distinct"] = {"value": None, "error": repr(ex)}
+        torch.cuda.empty_cache()
     if not args.no_e2e:
         # every rank runs the host-buffer path on its own GPU / PCIe link (rank r hashes its own files);
         # whole-job e2e = bytes of all ranks / slowest rank's time
@@ -368,9 +527,14 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                 "sample": f"{n_s} x {args.file_mib} MiB files of the same corpus, one stream per task, {th} threads "
                           f"(best of {cpu_thread_candidates(cores)} on {cores} logical CPUs), best of 2 ({dt:.2f} s)",
                 "note": "restated CPU baseline (oracle/oracle.c, SHA-NI), not the Go binary"}
+            try:
+                out["cpu_baseline"]["legs"] = cpu_legs_b1_b3()
+            except Exception as ex:
+                out["cpu_baseline"]["legs"] = {"error": repr(ex)}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
+        comm.close()
         dist.destroy_process_group()
     eng.close()
 
@@ -455,6 +619,11 @@ def run_e2e(args, eng, cfg, pg, torch, first_file=0):
     torch.cuda.empty_cache()
     off = np.arange(n, dtype=np.uint64) * file_len
     ln = np.full(n, file_len, dtype=np.uint64)
+    h2d_peak = None
+    try:
+        h2d_peak = h2d_roofline(torch, host)
+    except Exception:
+        pass
     sets = [e.digest_set(1 << 16) for e in engines]
     for e, s in zip(engines, sets):
         e.chunk_digest_batch(cfg, host, off, ln, s)      # warm-up (also populates each context's pools)
@@ -485,31 +654,75 @@ def run_e2e(args, eng, cfg, pg, torch, first_file=0):
         e.close()
     if errs:
         return {"value": None, "unit": "GiB/s", "error": errs[0]}
+    gbs = n * file_len * steps / dt / 1e9
     return {"value": n * file_len * steps / dt / GIB, "unit": "GiB/s", "h2d_bytes_per_step": int(n * file_len),
             "d2h_bytes_per_step": int(nrec[0] * 48), "steps": steps, "host_threads": workers, "seconds": dt,
+            "roofline": {"bound": "pcie_h2d", "achieved": gbs, "peak": h2d_peak, "unit": "GB/s",
+                         "frac": gbs / h2d_peak if h2d_peak else None,
+                         "peak_source": "pinned host -> device copy of 8 GiB measured in this run on this box (best of 3, CUDA events)"},
             "workload": f"{n} x {args.file_mib} MiB files of the cfg2 corpus per step (one blocking C-ABI call) from "
                         f"pinned host memory; PCIe-bound", "timer": "host wall clock around the blocking C-ABI calls"}
 
 
 def ncu_traffic():
-    """dram bytes (read+write) per launch of the SHA kernels from the committed ncu --set full summaries."""
+    """dram bytes (read + write) per launch of EVERY kernel class of the step, from the committed ncu --set full
+    summaries of one 64 GiB batch: K1 scan reads the input once, K3 (bulk + long-chunk kernel) reads it again."""
     import re
-    tot, used = 0.0, []
-    for name in ("r01_ncu_k_sha_tuned.txt", "r01_ncu_k_sha_split.txt"):
-        p = ROOT / "profiles" / name
-        if not p.exists():
-            return None, None
-        txt = p.read_text()
-        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-            m = re.search(key + r"\s+(\w+)\s+([0-9.]+)", txt)
-            if not m:
-                return None, None
-            scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(m.group(1), None)
-            if scale is None:
-                return None, None
-            tot += float(m.group(2)) * scale
-        used.append(name)
-    return tot, "profiles/" + " + ".join(used) + " (one 64 GiB batch; both SHA kernels of the hybrid launch)"
+    files = {"K1_scan": ("r01_ncu_k_scan_tuned.txt",), "K3_sha_bulk": ("r01_ncu_k_sha_tuned.txt",), "K3_sha_long": ("r01_ncu_k_sha_split.txt",)}
+    out, tot = {}, 0.0
+    for key, names in files.items():
+        for name in names:
+            p = ROOT / "profiles" / name
+            if not p.exists():
+                return None
+            txt = p.read_text()
+            b = 0.0
+            for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                mm = re.search(m + r"\s+(\w+)\s+([0-9.]+)", txt)
+                scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(mm.group(1)) if mm else None
+                if scale is None:
+                    return None
+                b += float(mm.group(2)) * scale
+            out[key] = b
+            tot += b
+    alg = 1024 * (64 << 20)
+    out.update({"total": tot, "algorithmic": alg, "ratio_to_algorithmic": tot / alg,
+                "source": "profiles/r01_ncu_k_scan_tuned.txt + r01_ncu_k_sha_tuned.txt + r01_ncu_k_sha_split.txt (one 64 GiB batch each); "
+                          "the input is read twice (K1, then K3): 2.0 x the algorithmic bytes; K7 (xxh3) is not part of the step"})
+    return out
+
+
+def run_cfg4verify(args):
+    """ONE GPU, ONE digest set: the global cfg4 corpus of `--emulate-ranks` x `--files` files hashed shard after shard in
+    global order.  Prints the entry bench.py's N > 1 arm compares its NCCL-merged hit count with
+    (profiles/r02_cfg4_expected.json)."""
+    import torch
+
+    import pbs_plus_b200 as pg
+
+    torch.cuda.set_device(0)
+    eng = pg.Engine(0)
+    file_len = args.file_mib << 20
+    corp = pg.corpus(seed=3, file_len=file_len, block_len=4 << 20, run_blocks=8, dup_permille=300)
+    cfg = pg.buzhash.NewConfig(4096)
+    entries = []
+    sub = 256                                   # files per batch
+    buf = torch.empty(sub * file_len, dtype=torch.uint8, device="cuda")
+    off = np.arange(sub, dtype=np.uint64) * file_len
+    ln = np.full(sub, file_len, dtype=np.uint64)
+    for world in [int(x) for x in args.emulate_ranks.split(",")]:
+        known = eng.digest_set(1 << 20)
+        chunks = hits = 0
+        for b in range(world * args.files // sub):
+            eng.corpus_fill(corp, b * sub, sub, buf, file_len)
+            rec = eng.chunk_digest_batch(cfg, buf, off, ln, known)
+            chunks += len(rec); hits += int((rec["flags"] & 1).sum())
+        entries.append({"world": world, "files_per_rank": args.files, "file_mib": args.file_mib, "chunks": chunks, "known": hits,
+                        "hit_rate": hits / max(1, chunks), "distinct": len(known)})
+        known.close()
+    print(json.dumps({"what": "cfg4 corpus (seed 3, 30 % dup 4 MiB blocks, runs of 8) through ONE set on one GPU, in global file order",
+                      "entries": entries}), flush=True)
+    eng.close()
 
 
 def main():
@@ -524,7 +737,11 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--e2e-threads", type=int, default=2)
     ap.add_argument("--avg-kib", type=int, default=4096, help="diagnostic only; the metric is quoted at 4096")
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4verify"])
+    ap.add_argument("--emulate-ranks", default="2,4,8", help="cfg4verify: world sizes to produce expected hit counts for")
+    ap.add_argument("--no-verify", action="store_true", help="skip the untimed post-run comparison with the oracle")
+    ap.add_argument("--no-distinct", action="store_true", help="skip the non-repeating-data figure (value_distinct)")
+    ap.add_argument("--distinct-gib", type=int, default=768)
     ap.add_argument("--total-tb", type=float, default=10.0, help="cfg3 only")
     ap.add_argument("--no-prewarm", action="store_true")
     ap.add_argument("--inflight", type=int, default=0,
@@ -539,6 +756,9 @@ def main():
     if args.workload == "cfg3":
         if rank == 0:
             run_cfg3(args)
+    elif args.workload == "cfg4verify":
+        if rank == 0:
+            run_cfg4verify(args)
     elif args.impl == "reference":
         run_reference(args, rank, world)
     else:

@@ -9,8 +9,16 @@ Inside WriteEntryReader the module pulls the reader's bytes, runs the buzhash sc
 cuts, SHA-256s every chunk, asks the session whether the digest is known and uploads
 only new chunks.  This mirror keeps the names and the pull-from-a-reader contract but
 batches the files: entries are queued and pushed through the GPU engine in one batch on
-Flush()/Finish().  pxar framing, blob encoding and the
-HTTP/2 upload are out of scope (section 8 a5, f3): `upload` is a callback.
+Flush()/Finish().  `upload` is a callback (the HTTP/2 upload is out of scope).
+
+Two writers:
+  * PayloadStreamWriter -- the LAYOUT-FAITHFUL one and the default for a drop-in: it produces the pxar v2 payload
+    stream the production chunker sees (PAYLOAD_START marker, then per file a 16-byte PAYLOAD header + content,
+    concatenated: internal/pxarmount/pxarfs.go:408-411), chunks THAT stream through pbsgpu_stream_* with a suggested
+    boundary at every file start, returns each entry's payload offset (what the mpxar PAYLOAD_REF stores) and
+    supports WriteEntryRef (chunk reuse from the previous .ppxar.didx, commit.go:752, :848-860).
+  * DedupWriter -- per-file batching (every file its own stream).  Faster for many small files, but its index does NOT
+    describe a ppxar payload stream: use it for dedup statistics / digest computation, not to write .ppxar.didx.
 """
 from __future__ import annotations
 
@@ -108,6 +116,131 @@ class DedupWriter:
         self.Flush()
         self._finished = True
         return self.index
+
+
+# pxar v2 format constants (upstream pxar crate format/mod.rs; restated, UNVERIFIED against the Go module)
+PXAR_PAYLOAD = 0x28147A1B0B7C1A25
+PXAR_PAYLOAD_START_MARKER = 0x834C68C2194A4ED2
+PXAR_PAYLOAD_TAIL_MARKER = 0x6C72B78B984C81B5
+
+
+def payload_header(content_len: int) -> bytes:
+    """16-byte PAYLOAD header: htype u64 LE, full_size u64 LE (header included) -- pxarfs.go:408-411 skips these 16."""
+    return PXAR_PAYLOAD.to_bytes(8, "little") + (16 + content_len).to_bytes(8, "little")
+
+
+class NotStrictlyGreater(IOError):
+    """WriteEntryRef out of order; the message carries the substring the reference matches (commit.go:849)."""
+
+
+@dataclass
+class PayloadStreamWriter:
+    """Writes ONE pxar v2 payload stream through the streaming C ABI (see the module docstring)."""
+    engine: Engine
+    config: Cfg
+    known: DigestSet | None = None
+    prev_index: tuple[np.ndarray, np.ndarray] | None = None   # (ends u64[], digests u8[n,32]) of the previous .ppxar.didx
+    suggest: bool = True             # suggested boundary at every file start (upstream PayloadChunker); False = plain chunker
+    index: list[tuple[int, bytes, bool]] = field(default_factory=list)   # (end offset in the NEW stream, digest, known)
+    payload_offsets: dict[str, int] = field(default_factory=dict)        # entry path -> offset of its PAYLOAD header
+    _stream: object = None
+    _seg_base: int = 0               # offset in the new stream at which the current pbsgpu stream starts
+    _last_ref: int = -1
+    _finished: bool = False
+
+    def __post_init__(self):
+        self._open()
+        self._raw(PXAR_PAYLOAD_START_MARKER.to_bytes(8, "little") + (16).to_bytes(8, "little"))
+
+    # -- plumbing ---------------------------------------------------------------------------------------------
+    def _open(self):
+        self._stream = self.engine.stream(self.config, self.known)
+
+    def _raw(self, data: bytes):
+        self._stream.write(np.frombuffer(data, dtype=np.uint8))
+
+    @property
+    def position(self) -> int:
+        return self._seg_base + self._stream.position
+
+    def _drain(self, final: bool):
+        rec = self._stream.finish() if final else self._stream.poll(1 << 16)
+        for r in rec:
+            self.index.append((self._seg_base + int(r["end_off"]), bytes(r["digest"]), bool(r["flags"] & CHUNK_KNOWN)))
+
+    # -- ArchiveWriter surface (commit.go:183) -------------------------------------------------------------------
+    def WriteEntryReader(self, entry: Entry, reader: BinaryIO, size: int) -> int:
+        """commit.go:720, :858.  Returns the entry's payload offset."""
+        if self._finished:
+            raise RuntimeError("transfer: writer already finished")
+        off = self.position
+        if self.suggest and self._stream.position > 0:
+            self._stream.suggest(self._stream.position)
+        self._raw(payload_header(size))
+        left = size
+        while left:
+            slot = self._stream.reserve()
+            want = min(left, len(slot))
+            data = reader.read(want)
+            if not data:
+                self._stream.commit(0)
+                raise IOError(f"transfer: short read for {entry.Path}: got {size - left} of {size} bytes (unexpected EOF)")
+            slot[: len(data)] = np.frombuffer(data, dtype=np.uint8)
+            self._stream.commit(len(data))
+            left -= len(data)
+        self.payload_offsets[entry.Path] = off
+        self._drain(False)
+        return off
+
+    def WriteEntryRef(self, entry: Entry, payload_offset: int) -> int:
+        """commit.go:752, :848: reuse the previous snapshot's chunks that hold [payload_offset, +16+FileSize) without
+        reading the content.  The running chunk is closed, the old chunks are appended to the new index (their bytes
+        become part of the new stream, padding included, as in upstream's chunk injection) and the entry's new payload
+        offset is returned.  Offsets must ascend; otherwise the error text contains "not strictly greater" and the
+        caller re-encodes through WriteEntryReader (commit.go:849-860)."""
+        if self.prev_index is None:
+            raise IOError("transfer: WriteEntryRef without a previous payload index")
+        if payload_offset <= self._last_ref:
+            raise NotStrictlyGreater(f"transfer: payload offset {payload_offset} not strictly greater than previous {self._last_ref}")
+        ends, digs = self.prev_index
+        lo = int(np.searchsorted(ends, payload_offset, side="right"))
+        hi = int(np.searchsorted(ends, payload_offset + 16 + entry.FileSize, side="left"))
+        if hi >= len(ends):
+            raise IOError(f"transfer: payload range of {entry.Path} lies outside the previous index")
+        # close the running chunk: the injected chunks start on a chunk boundary of the new stream
+        self._drain(True)
+        self._seg_base += self._stream.position
+        self._stream.close()
+        first_start = int(ends[lo - 1]) if lo else 0
+        pos = self._seg_base
+        for k in range(lo, hi + 1):
+            start = int(ends[k - 1]) if k else 0
+            pos += int(ends[k]) - start
+            self.index.append((pos, bytes(digs[k]), True))
+        new_off = self._seg_base + (payload_offset - first_start)
+        self._seg_base = pos
+        self._last_ref = payload_offset
+        self.payload_offsets[entry.Path] = new_off
+        self._open()
+        return new_off
+
+    def Finish(self) -> list[tuple[int, bytes, bool]]:
+        """commit.go:383: tail marker, final short chunk, index complete."""
+        if not self._finished:
+            self._raw(PXAR_PAYLOAD_TAIL_MARKER.to_bytes(8, "little") + (16).to_bytes(8, "little"))
+            self._drain(True)
+            self._stream.close()
+            self._finished = True
+        return self.index
+
+    def didx(self, uuid: bytes = b"\0" * 16, ctime: int = 0) -> bytes:
+        """The new .ppxar.didx image (csum on the GPU)."""
+        rec = np.zeros(len(self.index), dtype=CHUNK_DTYPE)
+        for i, (end, dig, known) in enumerate(self.index):
+            rec[i]["end_off"] = end
+            rec[i]["digest"] = np.frombuffer(dig, dtype=np.uint8)
+            rec[i]["flags"] = CHUNK_KNOWN if known else 0
+        return self.engine.didx_build(rec, uuid, ctime)
 
 
 def NewRemoteDedupSplitArchiveWriter(engine: Engine, config: Cfg, known: DigestSet | None = None,

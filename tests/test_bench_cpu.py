@@ -25,8 +25,27 @@ def test_union_of_overlapping_kernel_intervals():
 
 def test_traffic_is_read_from_committed_ncu_summaries():
     b = _bench()
-    tr, src = b.ncu_traffic()
-    assert tr is None or (6.0e10 < tr < 8.0e10 and "profiles/" in src)     # ~ one 64 GiB batch
+    tr = b.ncu_traffic()
+    if tr is not None:       # K1 reads the batch once, K3 (bulk + long kernel) reads it again: 2.0 x the algorithmic bytes
+        assert 1.9 < tr["ratio_to_algorithmic"] < 2.1 and "profiles/" in tr["source"]
+        assert abs(tr["total"] - (tr["K1_scan"] + tr["K3_sha_bulk"] + tr["K3_sha_long"])) < 1
+
+
+def test_instruction_ceiling_counts_every_sm():
+    b = _bench()
+    c = b.instr_ceiling(148, 1965.0, 500.0)
+    assert c["sm_count"] == 148 and 950 < c["alu_pipe_GBps"] < 1000 and abs(c["frac_of_alu_pipe"] - 500.0 / c["alu_pipe_GBps"]) < 1e-9
+    assert b.instr_ceiling(148, None, 1.0) is None
+
+
+def test_cfg4_expected_entries_are_found_by_shape(tmp_path, monkeypatch):
+    b = _bench()
+    (tmp_path / "profiles").mkdir()
+    (tmp_path / "profiles" / "r02_cfg4_expected.json").write_text(json.dumps({"entries": [
+        {"world": 2, "files_per_rank": 1024, "file_mib": 64, "chunks": 10, "known": 3}]}))
+    monkeypatch.setattr(b, "ROOT", tmp_path)
+    assert b.expected_cfg4_hits(2, 1024, 64)["known"] == 3
+    assert b.expected_cfg4_hits(4, 1024, 64) is None
 
 
 def test_reference_arm_prints_one_json_line():
