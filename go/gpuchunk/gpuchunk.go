@@ -106,9 +106,13 @@ type Chunk struct {
 	Digest [32]byte
 }
 
-// ErrStagingFull is returned by WriteEntryReader when the pinned staging buffer cannot take the entry:
+// ErrStagingFull is returned by WriteEntryReader when the pinned staging buffer cannot take the entry NOW:
 // Flush the batch and write the entry again.
 var ErrStagingFull = errors.New("pbsgpu: staging full, call Flush first")
+
+// ErrEntryTooLarge is returned when the entry alone exceeds the staging buffer: flushing cannot help, the entry has
+// to go through a Stream / PayloadWriter (which have no size limit).
+var ErrEntryTooLarge = errors.New("pbsgpu: entry larger than the staging buffer, use a Stream")
 
 // Batch accumulates whole files in C-owned PINNED staging (Go pointers are never retained by C)
 // and pushes them through the GPU in one call -- the batched form of the per-file loop at
@@ -134,6 +138,9 @@ func (e *Engine) NewBatch(cfg Config, stagingBytes uint64) (*Batch, error) {
 // WriteEntryReader mirrors transfer.ArchiveWriter.WriteEntryReader(entry, reader, size): it pulls
 // exactly size bytes from r (io.ReadFull semantics) into the staging buffer.
 func (b *Batch) WriteEntryReader(r io.Reader, size uint64) error {
+	if size > b.cap {
+		return ErrEntryTooLarge
+	}
 	start := (b.fill + 255) &^ 255
 	if start+size > b.cap {
 		return ErrStagingFull
@@ -267,6 +274,238 @@ func (b *Batch) BlobCRC32(off, length []uint64) ([]uint32, error) {
 	res := make([]uint32, n)
 	for i := range crc {
 		res[i] = uint32(crc[i])
+	}
+	return res, nil
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Streaming form: ONE byte stream of any length (a VM image, or the whole pxar payload stream), state carried
+// across writes -- the literal drop-in for writer.WriteEntryReader(entry, io.Reader, size) (commit.go:718-720).
+// ---------------------------------------------------------------------------------------------------------------
+
+// Stream wraps pbsgpu_stream_*.  Bytes travel through a pinned staging ring owned by the C side (reserve -> the
+// reader fills it -> commit starts the DMA); Go memory is never retained by C.
+type Stream struct {
+	e *Engine
+	s *C.pbsgpu_stream
+}
+
+func (e *Engine) NewStream(cfg Config, known *KnownSet) (*Stream, error) {
+	var set *C.pbsgpu_set
+	if known != nil {
+		set = known.s
+	}
+	var s *C.pbsgpu_stream
+	if err := e.err(C.pbsgpu_stream_open(e.ctx, &cfg.c, set, &s)); err != nil {
+		return nil, err
+	}
+	return &Stream{e, s}, nil
+}
+
+// ReadFrom pulls exactly size bytes from r straight into the pinned ring (io.ReadFull per slot), no intermediate copy.
+func (st *Stream) ReadFrom(r io.Reader, size uint64) error {
+	slot := uint64(C.pbsgpu_stream_slot_bytes(st.s))
+	for size > 0 {
+		var p unsafe.Pointer
+		if err := st.e.err(C.pbsgpu_stream_reserve(st.s, &p)); err != nil {
+			return err
+		}
+		n := size
+		if n > slot {
+			n = slot
+		}
+		if _, err := io.ReadFull(r, unsafe.Slice((*byte)(p), n)); err != nil {
+			C.pbsgpu_stream_commit(st.s, 0)
+			return fmt.Errorf("read payload: %w", err)
+		}
+		if err := st.e.err(C.pbsgpu_stream_commit(st.s, C.uint64_t(n))); err != nil {
+			return err
+		}
+		size -= n
+	}
+	return nil
+}
+
+// Write implements io.Writer (pageable Go memory is copied into the ring slot by slot).
+func (st *Stream) Write(p []byte) (int, error) {
+	if len(p) == 0 {
+		return 0, nil
+	}
+	if err := st.e.err(C.pbsgpu_stream_write(st.s, unsafe.Pointer(&p[0]), C.uint64_t(len(p)))); err != nil {
+		return 0, err
+	}
+	return len(p), nil
+}
+
+// Suggest registers a suggested boundary at the CURRENT position (call it right before writing a file's PAYLOAD header).
+func (st *Stream) Suggest() error {
+	return st.e.err(C.pbsgpu_stream_suggest(st.s, C.pbsgpu_stream_position(st.s)))
+}
+
+func (st *Stream) Position() uint64 { return uint64(C.pbsgpu_stream_position(st.s)) }
+
+// Poll returns the chunks finished so far (stream order); Finish flushes the final short chunk first.
+func (st *Stream) Poll() ([]Chunk, error) {
+	var all []Chunk
+	buf := make([]C.pbsgpu_chunk, 4096)
+	for {
+		var n C.uint64_t
+		if err := st.e.err(C.pbsgpu_stream_poll(st.s, &buf[0], C.uint64_t(len(buf)), &n)); err != nil {
+			return all, err
+		}
+		if n == 0 {
+			return all, nil
+		}
+		for i := 0; i < int(n); i++ {
+			var c Chunk
+			c.Known = buf[i].flags&C.PBSGPU_CHUNK_KNOWN != 0
+			c.End = uint64(buf[i].end_off)
+			copy(c.Digest[:], C.GoBytes(unsafe.Pointer(&buf[i].digest[0]), 32))
+			all = append(all, c)
+		}
+	}
+}
+
+func (st *Stream) Finish() ([]Chunk, error) {
+	if err := st.e.err(C.pbsgpu_stream_finish(st.s)); err != nil {
+		return nil, err
+	}
+	return st.Poll()
+}
+
+func (st *Stream) Close() { C.pbsgpu_stream_close(st.s) }
+
+// PayloadWriter produces the pxar v2 PAYLOAD stream the production chunker sees -- start marker, then per file a
+// 16-byte PAYLOAD header + content (internal/pxarmount/pxarfs.go:408-411) -- through ONE Stream, with a suggested
+// boundary at every file start.  WriteEntryReader returns the entry's payload offset (what the mpxar PAYLOAD_REF
+// stores).  This, not per-file batching, is the layout an existing .ppxar.didx describes.
+type PayloadWriter struct {
+	st      *Stream
+	Chunks  []Chunk
+	started bool
+}
+
+const (
+	pxarPayload            = 0x28147a1b0b7c1a25
+	pxarPayloadStartMarker = 0x834c68c2194a4ed2
+	pxarPayloadTailMarker  = 0x6c72b78b984c81b5
+)
+
+func header(htype, fullSize uint64) []byte {
+	var h [16]byte
+	for i := 0; i < 8; i++ {
+		h[i] = byte(htype >> (8 * i))
+		h[8+i] = byte(fullSize >> (8 * i))
+	}
+	return h[:]
+}
+
+func (e *Engine) NewPayloadWriter(cfg Config, known *KnownSet) (*PayloadWriter, error) {
+	st, err := e.NewStream(cfg, known)
+	if err != nil {
+		return nil, err
+	}
+	w := &PayloadWriter{st: st}
+	_, err = st.Write(header(pxarPayloadStartMarker, 16))
+	return w, err
+}
+
+func (w *PayloadWriter) WriteEntryReader(r io.Reader, size uint64) (payloadOffset uint64, err error) {
+	payloadOffset = w.st.Position()
+	if err = w.st.Suggest(); err != nil {
+		return
+	}
+	if _, err = w.st.Write(header(pxarPayload, 16+size)); err != nil {
+		return
+	}
+	if err = w.st.ReadFrom(r, size); err != nil {
+		return
+	}
+	done, err := w.st.Poll()
+	w.Chunks = append(w.Chunks, done...)
+	return
+}
+
+func (w *PayloadWriter) Finish() ([]Chunk, error) {
+	if _, err := w.st.Write(header(pxarPayloadTailMarker, 16)); err != nil {
+		return nil, err
+	}
+	done, err := w.st.Finish()
+	w.Chunks = append(w.Chunks, done...)
+	w.st.Close()
+	return w.Chunks, err
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Multi-GPU: one Engine per GPU (one goroutine each), files sharded by range; the ONE exchange step.
+// ---------------------------------------------------------------------------------------------------------------
+
+// NcclComm is an ncclComm_t made through the C ABI's helpers; a caller with its own NCCL binding passes its
+// communicator to AllGather through NcclCommFromHandle instead.
+type NcclComm struct{ h unsafe.Pointer }
+
+func NcclUniqueID() ([128]byte, error) {
+	var id [128]byte
+	if rc := C.pbsgpu_nccl_unique_id((*C.uint8_t)(unsafe.Pointer(&id[0]))); rc != 0 {
+		return id, fmt.Errorf("pbsgpu: NCCL unavailable (rc %d)", int(rc))
+	}
+	return id, nil
+}
+
+func (e *Engine) NewNcclComm(id [128]byte, nranks, rank int) (*NcclComm, error) {
+	var h unsafe.Pointer
+	if err := e.err(C.pbsgpu_nccl_comm_create(e.ctx, (*C.uint8_t)(unsafe.Pointer(&id[0])), C.int(nranks), C.int(rank), &h)); err != nil {
+		return nil, err
+	}
+	return &NcclComm{h}, nil
+}
+
+func NcclCommFromHandle(h unsafe.Pointer) *NcclComm { return &NcclComm{h} }
+func (c *NcclComm) Close()                           { C.pbsgpu_nccl_comm_destroy(c.h) }
+
+// AllGather merges this rank's chunk digests with every other rank's (pbsgpu_set_allgather: counts + padded
+// digests over NCCL/NVLink, then every replica inserts all of them in global (rank, index) order) and sets
+// Known on the chunks that are known globally.  Collective: every rank calls it once per batch.
+func (k *KnownSet) AllGather(comm *NcclComm, chunks []Chunk) error {
+	n := len(chunks)
+	dig := make([]byte, 32*n+1)
+	hit := make([]byte, n+1)
+	for i := range chunks {
+		copy(dig[32*i:], chunks[i].Digest[:])
+	}
+	rc := C.pbsgpu_set_allgather(k.s, comm.h, (*C.uint8_t)(unsafe.Pointer(&dig[0])), C.uint64_t(n), (*C.uint8_t)(unsafe.Pointer(&hit[0])))
+	if err := k.e.err(rc); err != nil {
+		return err
+	}
+	for i := range chunks {
+		chunks[i].Known = hit[i] != 0
+	}
+	return nil
+}
+
+// BlobEncode renders complete uncompressed DataBlobs (magic | crc32 | payload) for ranges of the batch's staging
+// buffer -- the upload bodies of the NEW chunks (POST /dynamic_chunk, internal/server/backup/log_cleanup.go:19-31).
+func (b *Batch) BlobEncode(off, length []uint64) ([][]byte, error) {
+	n := len(off)
+	if n == 0 {
+		return nil, nil
+	}
+	o := make([]C.uint64_t, n)
+	l := make([]C.uint64_t, n)
+	oo := make([]C.uint64_t, n)
+	var total uint64
+	for i := range off {
+		o[i], l[i], oo[i] = C.uint64_t(off[i]), C.uint64_t(length[i]), C.uint64_t(total)
+		total += uint64(C.pbsgpu_blob_size(C.uint64_t(length[i])))
+	}
+	out := make([]byte, total+1)
+	rc := C.pbsgpu_blob_encode_batch(b.e.ctx, b.buf, &o[0], &l[0], C.uint32_t(n), (*C.uint8_t)(unsafe.Pointer(&out[0])), &oo[0], nil)
+	if err := b.e.err(rc); err != nil {
+		return nil, err
+	}
+	res := make([][]byte, n)
+	for i := range off {
+		res[i] = out[uint64(oo[i]) : uint64(oo[i])+12+length[i]]
 	}
 	return res, nil
 }
