@@ -136,5 +136,81 @@ class DedupWriter {
     std::map<std::string, uint64_t> backed_hashes_;
 };
 
+// ---- the layout-faithful writer: ONE pxar v2 payload stream through pbsgpu_stream_* ---------------------------------
+// Start marker, then per file a 16-byte PAYLOAD header + content (reference internal/pxarmount/pxarfs.go:408-411),
+// chunker state carried across files, a suggested boundary at every file start, bytes read straight into the
+// library's pinned ring.  WriteEntryReader (commit.go:720) returns the entry's payload offset.
+struct PayloadChunk { uint64_t end_off; uint8_t digest[32]; bool known; };
+
+class PayloadStreamWriter {
+  public:
+    PayloadStreamWriter(Engine &e, const buzhash::Config &cfg, KnownSet *known, bool suggest = true)
+        : e_(e), suggest_(suggest) {
+        e.check(pbsgpu_stream_open(e.ctx(), &cfg, known ? known->handle() : nullptr, &s_));
+        raw(header(0x834c68c2194a4ed2ull, 16));                     // PXAR_PAYLOAD_START_MARKER
+    }
+    ~PayloadStreamWriter() { pbsgpu_stream_close(s_); }
+    PayloadStreamWriter(const PayloadStreamWriter &) = delete;
+    PayloadStreamWriter &operator=(const PayloadStreamWriter &) = delete;
+
+    uint64_t WriteEntryReader(const Entry &entry, const Reader &reader, uint64_t size) {
+        if (finished_) throw Error(PBSGPU_ESTATE, "transfer: writer already finished");
+        const uint64_t off = pbsgpu_stream_position(s_);
+        if (suggest_) e_.check(pbsgpu_stream_suggest(s_, off));
+        raw(header(0x28147a1b0b7c1a25ull, 16 + size));              // PXAR_PAYLOAD
+        const uint64_t slot = pbsgpu_stream_slot_bytes(s_);
+        uint64_t left = size;
+        while (left) {
+            void *p = nullptr;
+            e_.check(pbsgpu_stream_reserve(s_, &p));
+            const uint64_t want = left < slot ? left : slot;
+            uint64_t got = 0;
+            while (got < want) {
+                size_t k = reader((uint8_t *)p + got, want - got);
+                if (k == 0) { pbsgpu_stream_commit(s_, 0); throw Error(PBSGPU_EINVAL, "transfer: short read for " + entry.Path + ": unexpected EOF"); }
+                got += k;
+            }
+            e_.check(pbsgpu_stream_commit(s_, want));
+            left -= want;
+        }
+        drain();
+        return off;
+    }
+    const std::vector<PayloadChunk> &Finish() {
+        if (!finished_) {
+            raw(header(0x6c72b78b984c81b5ull, 16));                 // PXAR_PAYLOAD_TAIL_MARKER
+            e_.check(pbsgpu_stream_finish(s_));
+            drain();
+            finished_ = true;
+        }
+        return index_;
+    }
+
+  private:
+    static std::vector<uint8_t> header(uint64_t htype, uint64_t full) {
+        std::vector<uint8_t> h(16);
+        for (int i = 0; i < 8; i++) { h[i] = (uint8_t)(htype >> (8 * i)); h[8 + i] = (uint8_t)(full >> (8 * i)); }
+        return h;
+    }
+    void raw(const std::vector<uint8_t> &b) { e_.check(pbsgpu_stream_write(s_, b.data(), b.size())); }
+    void drain() {
+        pbsgpu_chunk buf[256];
+        for (;;) {
+            uint64_t n = 0;
+            e_.check(pbsgpu_stream_poll(s_, buf, 256, &n));
+            if (!n) break;
+            for (uint64_t i = 0; i < n; i++) {
+                PayloadChunk c; c.end_off = buf[i].end_off; std::memcpy(c.digest, buf[i].digest, 32);
+                c.known = (buf[i].flags & PBSGPU_CHUNK_KNOWN) != 0;
+                index_.push_back(c);
+            }
+        }
+    }
+    Engine &e_;
+    pbsgpu_stream *s_ = nullptr;
+    bool suggest_, finished_ = false;
+    std::vector<PayloadChunk> index_;
+};
+
 }  // namespace transfer
 }  // namespace pbsgpu

@@ -404,6 +404,19 @@ def test_cxx_host_mirror_driver(tmp_path):
     lines = out.stdout.strip().splitlines()
     assert lines[-1] == "config-error -22"
     ref = oracle.chunk_digest_streams(oracle.config(16 << 10), list(datas.values()))
+    pay = [l.split() for l in lines if l.startswith("payload ")]
+    pay_off = {l.split()[1]: int(l.split()[2]) for l in lines if l.startswith("payload-offset ")}
+    lines = [l for l in lines if not l.startswith("payload")]
+    # the layout-faithful writer: the same files as ONE pxar payload stream with suggested boundaries at the file starts
+    from pbs_plus_b200 import transfer as tr
+    parts, pos, starts = [tr.PXAR_PAYLOAD_START_MARKER.to_bytes(8, "little") + (16).to_bytes(8, "little")], 16, []
+    for v in datas.values():
+        starts.append(pos); parts += [tr.payload_header(len(v)), v.tobytes()]; pos += 16 + len(v)
+    parts.append(tr.PXAR_PAYLOAD_TAIL_MARKER.to_bytes(8, "little") + (16).to_bytes(8, "little"))
+    stream = np.frombuffer(b"".join(parts), dtype=np.uint8)
+    pref = oracle.chunk_digest_forced(oracle.config(16 << 10), stream, np.array(starts, np.uint64))
+    assert [(int(r[1]), r[2]) for r in pay] == [(int(r["end_off"]), bytes(r["digest"]).hex()) for r in pref]
+    assert pay_off == dict(zip(paths, starts))
     rows = [l.split() for l in lines[:-1] if not l.startswith("xxh3 ")]
     xx = {l.split()[1]: int(l.split()[2], 16) for l in lines if l.startswith("xxh3 ")}
     assert xx == {p: _xxh3_ref(v) for p, v in zip(paths, datas.values())}      # backedHashes mirror (commit.go:725)
