@@ -372,7 +372,8 @@ int pbsgpu_job_create(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg, const void *base_d
     j->want_digests = want_digests; j->variant = ctx->variant; j->profiling = ctx->profiling; j->set = set;
     j->off.assign(off, off + n); j->len.assign(len, len + n);
     const uint64_t tile = j->variant == 1 ? (uint64_t)SIMPLE_SPAN : (uint64_t)WARP_TILE;
-    j->scan_lanes = j->variant == 0 && ctx->scan_lanes;
+    // the lane-contiguous scan reads through a tensor map anchored at `base`: it needs a 128 B aligned base
+    j->scan_lanes = j->variant == 0 && ctx->scan_lanes && (((uintptr_t)j->base) & (scan_lanes_align() - 1)) == 0;
     const uint64_t super = scan_lanes_super_bytes(), super_steps = scan_lanes_steps();
     j->tile_first.resize(n + 1);
     uint64_t tiles = 0, total = 0, chunks = 0;
@@ -380,8 +381,8 @@ int pbsgpu_job_create(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg, const void *base_d
     for (uint32_t i = 0; i < n; i++) {
         if (len[i] >= (1ull << KEY_POS_BITS)) { delete j; return fail(ctx, PBSGPU_EINVAL, "stream %u longer than 2^40 bytes", i); }
         j->tile_first[i] = tiles;
-        if (j->scan_lanes) {   // k_scan_lanes: 8 steps per 64 KiB super-tile of a 16 B aligned stream, then plain tiles
-            const uint64_t ns = (((uintptr_t)(j->base + off[i])) & 15) == 0 ? len[i] / super : 0;
+        if (j->scan_lanes) {   // k_scan_lanes: 8 steps per 64 KiB super-tile of a 128 B aligned stream, then plain tiles
+            const uint64_t ns = (off[i] & (scan_lanes_align() - 1)) == 0 ? len[i] / super : 0;
             tiles += ns * super_steps + (len[i] - ns * super + tile - 1) / tile;
         } else {
             tiles += (len[i] + tile - 1) / tile;
@@ -452,7 +453,11 @@ int pbsgpu_job_enqueue_front(pbsgpu_job *j) {
     sa.total_tiles = j->total_tiles; sa.mask = j->cfg.mask; sa.break_min = j->cfg.break_min; sa.table = ctx->d_table;
     sa.cand = j->d_cand; sa.cand_cap = j->cand_cap; sa.cand_count = &j->d_counters[0];
     if (j->variant == 1) CK(launch_scan_simple(sa, st));
-    else if (j->scan_lanes) CK(launch_scan_lanes(sa, ctx->d_rot, ctx->sm_count, st));
+    else if (j->scan_lanes) {
+        uint64_t extent = 0;
+        for (uint32_t i = 0; i < n; i++) extent = std::max(extent, j->off[i] + j->len[i]);
+        CK(launch_scan_lanes(sa, ctx->d_rot, ctx->sm_count, extent, st));
+    }
     else CK(launch_scan_tuned(sa, ctx->d_rot, ctx->sm_count, st));
     if (j->d_forced) CK(launch_append_keys(j->d_forced, j->forced_keys.size(), j->d_cand, j->cand_cap, &j->d_counters[0], st));
     CK(cudaEventRecord(j->ev[EV_SCAN], st));

@@ -44,8 +44,9 @@ struct ScanArgs {
 };
 cudaError_t launch_scan_simple(const ScanArgs &a, cudaStream_t st);
 cudaError_t launch_scan_tuned(const ScanArgs &a, const uint32_t *rot_table /*[256][64]*/, int sm_count, cudaStream_t st);
-cudaError_t launch_scan_lanes(const ScanArgs &a, const uint32_t *rot_table, int sm_count, cudaStream_t st);
+cudaError_t launch_scan_lanes(const ScanArgs &a, const uint32_t *rot_table, int sm_count, uint64_t extent, cudaStream_t st);
 uint64_t scan_lanes_super_bytes();
+uint32_t scan_lanes_align();
 uint32_t scan_lanes_steps();
 cudaError_t launch_build_rot_table(const uint32_t *table, uint32_t *rot_table, cudaStream_t st);
 size_t scan_tuned_smem_bytes();

@@ -22,6 +22,7 @@
 //     byte: LOP3.LUT.PAND  P &= ((~(Q^Qold) & rotr(M21,.)) != 0)   (M21 = mask & ~3);
 //     only if P drops (p ~ 1e-4 per lane span) the lane re-walks its span exactly.
 //   => 3 ALU-pipe instructions per byte (PRMT, XOR, LOP3.PAND) + 1 LDS.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -130,13 +131,21 @@ __device__ __forceinline__ void test_acc(uint32_t a, uint32_t b, uint32_t c, uin
         : "r"(a), "r"(b), "r"(c));
 }
 
-// 64 bytes of one lane: 4 x LDS.128 of data, per byte PRMT -> LDS(rot) -> XOR (-> test)
-template <bool TEST, int NVEC>
+// 64 bytes of one lane: 4 x LDS.128 of data, per byte PRMT -> LDS(rot) -> XOR (-> test).
+// SWZ: the lane's 256 B piece lies in a SWIZZLE_128B tensor-map tile [half][lane][128 B]: vector V (0..15) of the piece
+// is at row + (V >> 3) * 4096 + (((V & 7) ^ sw) << 4), sw = lane & 7 (`data` = row, `v0` = first vector of this block).
+template <bool TEST, int NVEC, bool SWZ = false>
 __device__ __forceinline__ void lane_block(const uint4 *data, const uint8_t *rotb, uint32_t laneoff, uint32_t (&Q)[64],
-                                           const uint32_t (&M)[32], uint32_t &q, uint32_t &acc) {
+                                           const uint32_t (&M)[32], uint32_t &q, uint32_t &acc, uint32_t v0 = 0, uint32_t sw = 0) {
 #pragma unroll
     for (int v = 0; v < NVEC; v++) {
-        uint4 d = data[v];
+        uint4 d;
+        if (SWZ) {
+            const uint32_t V = v0 + v;
+            d = *(const uint4 *)((const uint8_t *)data + ((V >> 3) << 12) + (((V & 7) ^ sw) << 4));
+        } else {
+            d = data[v];
+        }
         uint32_t w[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
         for (int j = 0; j < 16; j++) {
@@ -287,10 +296,15 @@ constexpr int LS_R = 2048;                    // bytes per lane per super-tile
 constexpr int LS_PIECE = 256;
 constexpr int LS_STEPS = LS_R / LS_PIECE;     // 8
 constexpr int LS_SUPER = 32 * LS_R;           // 64 KiB
-constexpr int LS_HALO_STRIDE = 80;            // 64 B halo + 16 B pad: conflict-free LDS.128 (5 quads)
-constexpr int LS_SMEM = ROT_BYTES + WARPS_PER_CTA * (2 * BUF_STRIDE + 32 * LS_HALO_STRIDE) + WARPS_PER_CTA * 2 * 8;
+constexpr int LS_HALO_STRIDE = 64;            // per-lane halo rows behind the 8 KiB box (read 4 x per 8 steps: conflicts do not matter)
+constexpr int LS_BUF = 10240;                 // step buffer: 8 KiB tensor-map box (1024 B aligned for SWIZZLE_128B) + 2 KiB halo;
+                                              // a plain 8704 B tile (+64 B halo) fits too
+constexpr int LS_BOX = 32 * LS_PIECE;         // 8192
+constexpr int LS_SMEM = ROT_BYTES + WARPS_PER_CTA * 2 * LS_BUF + WARPS_PER_CTA * 2 * 8;
+constexpr uint32_t LS_ALIGN = 128;            // a stream takes super-tiles only if it starts on a 128 B unit of the tensor map
 
 uint64_t scan_lanes_super_bytes() { return LS_SUPER; }
+uint32_t scan_lanes_align() { return LS_ALIGN; }
 uint32_t scan_lanes_steps() { return LS_STEPS; }
 
 struct StepInfo {
@@ -303,8 +317,12 @@ struct StepInfo {
 
 // Exact walk of one lane's 256 B piece (slow path of k_scan_lanes).  The piece is in shared memory; the 64 bytes
 // before it left shared memory a step ago, so they come back from global memory (L2) as four 16 B loads.
-__device__ __noinline__ void piece_exact(const ScanArgs &a, const uint8_t *piece, const uint32_t *rot, uint32_t lane,
+// `row` = the lane's 128 B row of half 0 in the swizzled tile; byte p of the piece is at
+// row + (p >> 7) * 4096 + ((((p >> 4) & 7) ^ sw) << 4) + (p & 15).
+__device__ __noinline__ void piece_exact(const ScanArgs &a, const uint8_t *row, const uint32_t *rot, uint32_t lane,
                                          uint32_t stream, const uint8_t *d, uint64_t start) {
+    const uint32_t sw = lane & 7;
+    auto piece_at = [&](int p) -> uint32_t { return row[((p >> 7) << 12) + ((((p >> 4) & 7) ^ sw) << 4) + (p & 15)]; };
     uint4 hv[4];
     if (start >= 64) {
         const uint4 *g = (const uint4 *)(d + start - 64);   // stream start and `start` are multiples of 16
@@ -318,15 +336,16 @@ __device__ __noinline__ void piece_exact(const ScanArgs &a, const uint8_t *piece
     uint32_t h = 0;
     for (int p = 0; p < 64; p++) h = rotl32(h, 1) ^ rotl32(rot[halo[p] * ROT_SLOTS + lane], lane);
     for (int p = 0; p < LS_PIECE; p++) {
-        const uint32_t leave = p < 64 ? halo[p] : piece[p - 64];
-        h = rotl32(h, 1) ^ rotl32(rot[piece[p] * ROT_SLOTS + lane], lane) ^ rotl32(rot[leave * ROT_SLOTS + lane], lane);
+        const uint32_t leave = p < 64 ? halo[p] : piece_at(p - 64);
+        h = rotl32(h, 1) ^ rotl32(rot[piece_at(p) * ROT_SLOTS + lane], lane) ^ rotl32(rot[leave * ROT_SLOTS + lane], lane);
         const uint64_t pos = start + (uint32_t)p;
         if (pos >= 63 && (h & a.mask) >= a.break_min) emit_candidate(a, stream, pos);
     }
 }
 
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 1) k_scan_lanes(ScanArgs a, const uint32_t *__restrict__ rot_g) {
-    extern __shared__ __align__(128) uint8_t smem[];
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 1) k_scan_lanes(ScanArgs a, const uint32_t *__restrict__ rot_g,
+                                                                       const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(1024) uint8_t smem[];
     uint32_t *rot = (uint32_t *)smem;
     const uint8_t *rotb = smem;
     {
@@ -335,9 +354,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 1) k_scan_lanes(ScanArgs a
         for (int i = threadIdx.x; i < ROT_BYTES / 16; i += blockDim.x) dst[i] = src[i];
     }
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t *buf0 = smem + ROT_BYTES + warp * (2 * BUF_STRIDE + 32 * LS_HALO_STRIDE);
-    uint8_t *halo_buf = buf0 + 2 * BUF_STRIDE;
-    uint64_t *bars = (uint64_t *)(smem + ROT_BYTES + WARPS_PER_CTA * (2 * BUF_STRIDE + 32 * LS_HALO_STRIDE)) + warp * 2;
+    uint8_t *buf0 = smem + ROT_BYTES + warp * 2 * LS_BUF;          // ROT_BYTES = 64 KiB: every step buffer is 1024 B aligned
+    uint64_t *bars = (uint64_t *)(smem + ROT_BYTES + WARPS_PER_CTA * 2 * LS_BUF) + warp * 2;
     const uint32_t bar_s[2] = {smem_u32(&bars[0]), smem_u32(&bars[1])};
     if (lane == 0) {
         mbar_init(bar_s[0], 1);
@@ -347,7 +365,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 1) k_scan_lanes(ScanArgs a
     __syncthreads();
     const uint64_t gw = (uint64_t)blockIdx.x * WARPS_PER_CTA + warp, nw = (uint64_t)gridDim.x * WARPS_PER_CTA;
     auto n_super_of = [&](uint32_t sc) -> uint64_t {
-        return (((uintptr_t)(a.base + a.off[sc])) & 15) == 0 ? a.len[sc] / LS_SUPER : 0;
+        return (a.off[sc] & (LS_ALIGN - 1)) == 0 ? a.len[sc] / LS_SUPER : 0;   // a.base itself is 128 B aligned (host checked)
     };
     // warps split the step list evenly, but a split inside a super-tile moves back to the super-tile's step 0
     auto round_unit = [&](uint64_t x) -> uint64_t {
@@ -387,25 +405,31 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 1) k_scan_lanes(ScanArgs a
         return true;
     };
     auto issue = [&](const StepInfo &st, int b) {
-        uint8_t *buf = buf0 + b * BUF_STRIDE;
+        uint8_t *buf = buf0 + b * LS_BUF;
         const uint8_t *sbase = a.base + a.off[st.stream];
         if (st.kind == 1) {
+            // ONE tensor-map copy brings the 256 B piece of every lane: box {128 B, 1, 32 lanes (stride 2 KiB), 2 halves},
+            // SWIZZLE_128B -> shared [half][lane][128 B] (SASS UTMALDG); only step 0 adds the per-lane 64 B halos.
             const uint64_t lane_start = st.stream_pos + (uint64_t)lane * LS_R;
             const bool first_of_stream = st.k == 0 && lane_start == 0;      // only lane 0 of the stream's first super-tile
-            if (st.k == 0 && first_of_stream) {
-                uint32_t *hz = (uint32_t *)(halo_buf + lane * LS_HALO_STRIDE);
+            uint8_t *halo = buf + LS_BOX + lane * LS_HALO_STRIDE;
+            if (first_of_stream) {
+                uint32_t *hz = (uint32_t *)halo;
 #pragma unroll
                 for (int i = 0; i < 16; i++) hz[i] = 0;                     // zero halo (positions < 63 are never reported)
             }
             const uint32_t any_first = __ballot_sync(0xffffffffu, first_of_stream);
-            uint32_t bytes = 32 * LS_PIECE + (st.k == 0 ? (32 - __popc(any_first)) * 64 : 0);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // this lane's earlier reads of the buffer
+            const uint32_t bytes = LS_BOX + (st.k == 0 ? (32 - __popc(any_first)) * 64 : 0);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // this lane's earlier reads / writes of the buffer
             __syncwarp();
-            if (lane == 0) mbar_arrive_expect_tx(bar_s[b], bytes);
+            if (lane == 0) {
+                mbar_arrive_expect_tx(bar_s[b], bytes);
+                const int c1 = (int)((a.off[st.stream] + st.stream_pos + (uint64_t)st.k * LS_PIECE) >> 7);   // 128 B unit of lane 0's piece
+                asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                             ::"r"(smem_u32(buf)), "l"(&tmap), "r"(0), "r"(c1), "r"(0), "r"(0), "r"(bar_s[b]) : "memory");
+            }
             __syncwarp();
-            tma_bulk_g2s(smem_u32(buf + lane * LANE_SPAN), sbase + lane_start + (uint64_t)st.k * LS_PIECE, LS_PIECE, bar_s[b]);
-            if (st.k == 0 && !first_of_stream)
-                tma_bulk_g2s(smem_u32(halo_buf + lane * LS_HALO_STRIDE), sbase + lane_start - 64, 64, bar_s[b]);
+            if (st.k == 0 && !first_of_stream) tma_bulk_g2s(smem_u32(halo), sbase + lane_start - 64, 64, bar_s[b]);
         } else {
             const uint8_t *src = sbase + st.stream_pos;
             uint32_t halo = st.stream_pos ? HALO : 0;
@@ -440,18 +464,18 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 1) k_scan_lanes(ScanArgs a
         const bool have_next = next_step(nxt);
         if (have_next) issue(nxt, b ^ 1);
         mbar_wait(bar_s[b], (uint32_t)((n >> 1) & 1));
-        const uint8_t *buf = buf0 + b * BUF_STRIDE;
+        const uint8_t *buf = buf0 + b * LS_BUF;
         uint32_t acc = 1;
         if (cur.kind == 1) {
-            const uint4 *data = (const uint4 *)(buf + lane * LANE_SPAN);
+            const uint4 *row = (const uint4 *)(buf + lane * 128);      // the lane's row of half 0 in the swizzled tile
             if (cur.k == 0) {
                 q = 0;
-                lane_block<false, 4>((const uint4 *)(halo_buf + lane * LS_HALO_STRIDE), rotb, laneoff, Q, M, q, acc);
+                lane_block<false, 4>((const uint4 *)(buf + LS_BOX + lane * LS_HALO_STRIDE), rotb, laneoff, Q, M, q, acc);
             }
 #pragma unroll 1
-            for (int it = 0; it < 4; it++) lane_block<true, 4>(data + it * 4, rotb, laneoff, Q, M, q, acc);
+            for (int it = 0; it < 4; it++) lane_block<true, 4, true>(row, rotb, laneoff, Q, M, q, acc, (uint32_t)it * 4, lane & 7);
             if (!acc)
-                piece_exact(a, buf + lane * LANE_SPAN, rot, lane, cur.stream, a.base + a.off[cur.stream],
+                piece_exact(a, (const uint8_t *)row, rot, lane, cur.stream, a.base + a.off[cur.stream],
                             cur.stream_pos + (uint64_t)lane * LS_R + (uint64_t)cur.k * LS_PIECE);
         } else {
             TileInfo ti;
@@ -474,13 +498,37 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 1) k_scan_lanes(ScanArgs a
     }
 }
 
-cudaError_t launch_scan_lanes(const ScanArgs &a, const uint32_t *rot_table, int sm_count, cudaStream_t st) {
+typedef CUresult (*tmap_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// `extent` = bytes of the batch buffer behind a.base that streams may touch (max off + len).  a.base must be 128 B aligned
+// (the caller routes other bases to k_scan_tuned).
+cudaError_t launch_scan_lanes(const ScanArgs &a, const uint32_t *rot_table, int sm_count, uint64_t extent, cudaStream_t st) {
     if (a.total_tiles == 0) return cudaSuccess;
+    static tmap_encode_fn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn ||
+            qr != cudaDriverEntryPointSuccess) { (void)cudaGetLastError(); return cudaErrorNotSupported; }
+        encode = (tmap_encode_fn)fn;
+    }
+    // u8 tensor over the batch: dim0 = 128 contiguous bytes, dim1 = 128 B unit index, dim2 = lane (stride 2 KiB),
+    // dim3 = half (stride 128 B); overlapping strides on purpose (profiles/r02_tma_tensor_probe.txt)
+    CUtensorMap tmap;
+    const cuuint64_t units = extent / 128 ? extent / 128 : 1;
+    const cuuint64_t dims[4] = {128, units, 32, 2};
+    const cuuint64_t strides[3] = {128, LS_R, 128};
+    const cuuint32_t box[4] = {128, 1, 32, 2}, estr[4] = {1, 1, 1, 1};
+    if (encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, (void *)a.base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(k_scan_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, LS_SMEM);
     if (e != cudaSuccess) return e;
     uint64_t want = (a.total_tiles + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     unsigned grid = (unsigned)(want < (uint64_t)sm_count ? want : (uint64_t)sm_count);
-    k_scan_lanes<<<grid, WARPS_PER_CTA * 32, LS_SMEM, st>>>(a, rot_table);
+    k_scan_lanes<<<grid, WARPS_PER_CTA * 32, LS_SMEM, st>>>(a, rot_table, tmap);
     return cudaGetLastError();
 }
 

@@ -213,6 +213,10 @@ static const Variant VS[] = {
     {"v11                                 128 thr, <=64 regs", lab<11, 128, 8>},
     {"v27                                 128 thr, <=64 regs", lab<27, 128, 8>},
     {"v11                                 256 thr, <=64 regs", lab<11, 256, 4>},
+    {"v27                                  64 thr, <=64 regs", lab<27, 64, 16>},
+    {"v27                                 128 thr, <=56 regs", lab<27, 128, 9>},
+    {"v11                                 128 thr, <=48 regs", lab<11, 128, 10>},
+    {"v0                                  128 thr, <=48 regs", lab<0, 128, 10>},
     {"product k_sha_tuned<2>", prod_tuned<2>},
     {"product k_sha_tuned<3>", prod_tuned<3>},
     {"product k_sha_split<3,0>", prod_split<3, 0>},
@@ -291,7 +295,12 @@ int main(int argc, char **argv) {
         // load curve: C concurrent chains of equal length; time per 64 B block of a chain = the chain latency that bounds
         // a batch's makespan, GB/s = throughput at that load.  C = 148 SMs x 4 sub-partitions x 32 lanes x {1/4 .. 8} warps.
         const uint64_t chain = (argc > 2 ? atoll(argv[2]) : 1024) << 10;   // bytes per chain
-        const int picks[] = {0, 3, 4, 17, 19, 20};                          // v0, v11, v27, tuned<2>, split<3,0>, split<3,1>
+        int picks[6] = {0, 3, 4, -1, -1, -1};                               // v0, v11, v27, then tuned<2>, split<3,0>, split<3,1> by name
+        for (int v = 0; v < NV; v++) {
+            if (!strcmp(VS[v].name, "product k_sha_tuned<2>")) picks[3] = v;
+            if (!strcmp(VS[v].name, "product k_sha_split<3,0>")) picks[4] = v;
+            if (!strcmp(VS[v].name, "product k_sha_split<3,1>")) picks[5] = v;
+        }
         const uint32_t base_c = (uint32_t)sms * 4 * 32;
         const double mult[] = {0.25, 0.5, 1, 2, 4, 8};
         const uint32_t max_n = (uint32_t)(base_c * 8);
