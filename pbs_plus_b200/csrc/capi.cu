@@ -150,6 +150,7 @@ static void ctx_destroy(pbsgpu_ctx *ctx) {
         if (ctx->streams2[i]) cudaStreamDestroy(ctx->streams2[i]);
     }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->tail_stream) cudaStreamDestroy(ctx->tail_stream);
     if (ctx->d_table) cudaFree(ctx->d_table);
     if (ctx->d_rot) cudaFree(ctx->d_rot);
     if (ctx->d_crc_tables) cudaFree(ctx->d_crc_tables);
@@ -209,7 +210,8 @@ extern "C" int pbsgpu_open(int device, pbsgpu_ctx **out) {
         for (int i = 0; i < N_STREAMS && !partitioned && ok; i++)
             ok = cudaStreamCreateWithFlags(&ctx->streams[i], cudaStreamNonBlocking) == cudaSuccess &&
                  cudaStreamCreateWithPriority(&ctx->streams2[i], cudaStreamNonBlocking, side_prio) == cudaSuccess;
-        if (!ok || cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { rc = PBSGPU_ECUDA; break; }
+        if (!ok || cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&ctx->tail_stream, cudaStreamNonBlocking) != cudaSuccess) { rc = PBSGPU_ECUDA; break; }
         ctx->streams_made = true;
         if (cudaMalloc(&ctx->d_table, 1024) != cudaSuccess || cudaMalloc(&ctx->d_rot, 65536) != cudaSuccess) { rc = PBSGPU_ENOMEM; break; }
         if (cudaEventCreate(&ctx->epoch) != cudaSuccess || cudaEventRecord(ctx->epoch, ctx->streams[0]) != cudaSuccess ||
@@ -283,6 +285,7 @@ static int upload_table(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg, cudaStream_t st)
 void pbsgpu_job_release(pbsgpu_job *j) {
     if (!j) return;
     pbsgpu_ctx *c = j->ctx;
+    if (j->enqueued && j->have_events) { cudaEventSynchronize(j->ev[EV_END]); (void)cudaGetLastError(); }   // the tail may run on the tail stream
     if (j->set && j->enqueued && !j->reconciled) {   // abandoned after its probe was enqueued: settle the set's bookkeeping
         cudaStreamSynchronize(j->st);
         pbsgpu_set_reconcile(j->set, j->chunk_cap, j->h_counters ? j->h_counters[3] : 0);
@@ -516,21 +519,25 @@ int pbsgpu_job_enqueue_back(pbsgpu_job *j) {
             if (!serial) CK(cudaStreamWaitEvent(st, j->ev[EV_JOIN], 0));
         }
     }
-    if (j->profiling) CK(cudaEventRecord(j->ev[EV_SHA], st));
+    CK(cudaEventRecord(j->ev[EV_SHA], st));
+    // The job's tail -- K4 (fused probe + insert), pack, D2H -- runs on the context's ONE tail stream when a set is
+    // attached: jobs that share a set are thereby ordered in submission order without holding each other's streams
+    // (a job's own stream is free for the slot's next job as soon as its SHA-256 is done).
+    cudaStream_t ts = (j->set && j->want_digests) ? ctx->tail_stream : st;
+    if (ts != st) CK(cudaStreamWaitEvent(ts, j->ev[EV_SHA], 0));
     if (j->set && j->want_digests) {
-        // K4 on the job's stream, ordered behind every earlier operation on the same table
         int rc = pbsgpu_set_enqueue_fused(j->set, j->d_digests, &j->d_counters[1], j->chunk_cap, &j->d_counters[0], j->cand_cap,
-                                          j->d_hit, &j->d_counters[3], j->d_set_scratch, st);
+                                          j->d_hit, &j->d_counters[3], j->d_set_scratch, ts);
         if (rc) return rc;
     }
-    if (j->profiling) CK(cudaEventRecord(j->ev[EV_SET], st));
+    if (j->profiling) CK(cudaEventRecord(j->ev[EV_SET], ts));
     if (j->want_digests)
-        CK(launch_pack_chunks(j->d_chunks, j->d_digests, j->set ? j->d_hit : nullptr, &j->d_counters[1], j->chunk_cap, j->d_out, st));
-    CK(cudaMemcpyAsync(j->h_counters, j->d_counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CK(launch_pack_chunks(j->d_chunks, j->d_digests, j->set ? j->d_hit : nullptr, &j->d_counters[1], j->chunk_cap, j->d_out, ts));
+    CK(cudaMemcpyAsync(j->h_counters, j->d_counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ts));
     if (j->want_digests)
-        CK(cudaMemcpyAsync(j->h_out, j->d_out, sizeof(pbsgpu_chunk) * j->chunk_cap, cudaMemcpyDeviceToHost, st));
-    if (!j->eof && n) CK(cudaMemcpyAsync(j->h_consumed, j->d_consumed, n * 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaEventRecord(j->ev[EV_END], st));
+        CK(cudaMemcpyAsync(j->h_out, j->d_out, sizeof(pbsgpu_chunk) * j->chunk_cap, cudaMemcpyDeviceToHost, ts));
+    if (!j->eof && n) CK(cudaMemcpyAsync(j->h_consumed, j->d_consumed, n * 8, cudaMemcpyDeviceToHost, ts));
+    CK(cudaEventRecord(j->ev[EV_END], ts));
     j->enqueued = true;
     j->back_done = true;
     j->reconciled = false;

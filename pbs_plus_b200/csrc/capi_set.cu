@@ -53,13 +53,19 @@ extern "C" void pbsgpu_set_destroy(pbsgpu_set *s) {
 // Digests in the table as far as finished operations go (a fused batch probe counts once its job was collected).
 extern "C" int pbsgpu_set_count(pbsgpu_set *s, uint64_t *count) { if (!s || !count) return PBSGPU_EINVAL; *count = s->count; return 0; }
 
-// keep the load <= 50 % for `more` further insertions; rehashing waits for every operation enqueued on the table
+// Capacity rule.  Insertions never fail as long as the table has a free slot, so the HARD requirement is
+//     count + pending_max + more <= 7/8 * cap        (pending_max = worst-case insertions of operations still in flight)
+// and the COMFORT target is a load <= 50 % of what is really in the table (count).  The worst case of a fused batch
+// probe is its launch bound (bytes / min chunk size), 3.6 x what random data produces -- using it for the comfort
+// target made the table grow (and the host wait for every operation in flight) in the middle of a pipelined run.
+// Rehashing waits for every operation enqueued on the table.
 static int set_reserve(pbsgpu_set *s, uint64_t more, cudaStream_t st) {
     pbsgpu_ctx *ctx = s->ctx;
-    const uint64_t need = s->count + s->pending_max + more;
-    if (need * 2 <= s->t.cap) return PBSGPU_OK;
+    const uint64_t hard = s->count + s->pending_max + more;
+    const uint64_t soft = s->count + (s->pending_max + more) / 4;
+    if (hard <= s->t.cap / 8 * 7 && soft * 2 <= s->t.cap) return PBSGPU_OK;
     uint64_t cap = s->t.cap;
-    while (need * 2 > cap) cap <<= 1;
+    while (hard > cap / 8 * 7 || soft * 2 > cap) cap <<= 1;
     if (s->last_valid) CK(cudaEventSynchronize(s->last));
     SetTable nt;
     int rc = set_alloc_table(ctx, cap, &nt, st);

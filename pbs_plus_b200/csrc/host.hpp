@@ -49,6 +49,7 @@ struct pbsgpu_ctx {
     cudaStream_t streams[N_STREAMS] = {};
     cudaStream_t streams2[N_STREAMS] = {};   // forked side stream per job stream (latency kernel of the hybrid SHA launch)
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t tail_stream = nullptr;     // K4 (fused probe) + pack + D2H of every job, in submission order
     bool streams_made = false;
     int next_stream = 0;
     Pool dev, pin;
