@@ -123,7 +123,7 @@ static bool make_partition(pbsgpu_ctx *ctx, int want) {
     if (gcreate(&ctx->g_bulk, dB, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return false;
     cudaStream_t a[N_STREAMS] = {}, b[N_STREAMS] = {};
     bool ok = true;
-    for (int i = 0; i < N_STREAMS && ok; i++) {
+    for (int i = 0; i < ctx->n_slots && ok; i++) {
         CUstream sa = nullptr, sb = nullptr;
         ok = gstream(&sb, ctx->g_bulk, CU_STREAM_NON_BLOCKING, 0) == CUDA_SUCCESS;
         if (ok) b[i] = (cudaStream_t)sb;
@@ -197,6 +197,8 @@ extern "C" int pbsgpu_open(int device, pbsgpu_ctx **out) {
         ctx->tune.thr_x10 = env_int("PBSGPU_HYBRID_THR_X10", ctx->tune.thr_x10);
         ctx->tune.serial = env_int("PBSGPU_HYBRID_SERIAL", ctx->tune.serial);
         ctx->tune.spread_kb = env_int("PBSGPU_SPLIT_SPREAD_KB", ctx->tune.spread_kb);
+        ctx->tune.head_per_sm = std::max(1, env_int("PBSGPU_HYBRID_HEAD_PER_SM", ctx->tune.head_per_sm));
+        ctx->n_slots = std::max(1, std::min(N_STREAMS, env_int("PBSGPU_SLOTS", ctx->n_slots)));
         ctx->crc_variant = env_int("PBSGPU_CRC_VARIANT", 0);
         if (getenv("PBSGPU_STREAM_WINDOW")) ctx->stream_window = strtoull(getenv("PBSGPU_STREAM_WINDOW"), nullptr, 0);
         ctx->stream_nbuf = std::max(2, std::min(32, env_int("PBSGPU_STREAM_NBUF", ctx->stream_nbuf)));
@@ -207,7 +209,7 @@ extern "C" int pbsgpu_open(int device, pbsgpu_ctx **out) {
         const int want_part = env_int("PBSGPU_PARTITION_SMS", 24);
         const bool partitioned = want_part > 0 && want_part + 8 <= ctx->sm_count && make_partition(ctx, want_part);
         bool ok = true;
-        for (int i = 0; i < N_STREAMS && !partitioned && ok; i++)
+        for (int i = 0; i < ctx->n_slots && !partitioned && ok; i++)
             ok = cudaStreamCreateWithFlags(&ctx->streams[i], cudaStreamNonBlocking) == cudaSuccess &&
                  cudaStreamCreateWithPriority(&ctx->streams2[i], cudaStreamNonBlocking, side_prio) == cudaSuccess;
         if (!ok || cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -412,7 +414,7 @@ int pbsgpu_job_create(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg, const void *base_d
     if (j->cand_cap >= (1ull << 31)) { delete j; return fail(ctx, PBSGPU_EINVAL, "batch too large (candidate buffer)"); }
     j->st = ctx->streams[ctx->next_stream];
     j->st2 = ctx->streams2[ctx->next_stream];
-    ctx->next_stream = (ctx->next_stream + 1) % N_STREAMS;
+    ctx->next_stream = (ctx->next_stream + 1) % ctx->n_slots;
     int rc = job_alloc(j);
     if (rc) { pbsgpu_job_release(j); return rc; }
     for (int i = 0; i < EV_COUNT; i++)
@@ -507,7 +509,7 @@ int pbsgpu_job_enqueue_back(pbsgpu_job *j) {
             uint64_t thr64 = (uint64_t)j->cfg.avg * (uint64_t)ctx->tune.thr_x10 / 10;
             uint32_t thr = thr64 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)thr64;
             // at most one latency CTA (32 chunks) per SM of the partition and job; the longest chunks first
-            const unsigned long long max_head = 32ull * (unsigned long long)(ctx->part_sms > 0 ? ctx->part_sms : 24);
+            const unsigned long long max_head = (unsigned long long)ctx->tune.head_per_sm * (unsigned long long)(ctx->part_sms > 0 ? ctx->part_sms : 24);
             CK(launch_split_point(j->d_keys2, &j->d_counters[1], j->chunk_cap, thr, max_head, &j->d_counters[2], st));
             CK(cudaEventRecord(j->ev[EV_FORK], st));
             if (!serial) CK(cudaStreamWaitEvent(side, j->ev[EV_FORK], 0));

@@ -36,7 +36,7 @@ struct Scoped {
     explicit operator bool() const { return p != nullptr; }
 };
 
-constexpr int N_STREAMS = 13;   // main + side stream per slot: 26 streams (+ copy stream) <= 32 HW connections
+constexpr int N_STREAMS = 15;   // upper bound of stream slots (main + side stream each); 2 x 15 + copy + tail = 32 HW connections
 
 struct pbsgpu_job;
 struct pbsgpu_ctx {
@@ -52,6 +52,7 @@ struct pbsgpu_ctx {
     cudaStream_t tail_stream = nullptr;     // K4 (fused probe) + pack + D2H of every job, in submission order
     bool streams_made = false;
     int next_stream = 0;
+    int n_slots = 13;        // PBSGPU_SLOTS: slots in use (jobs of one slot queue FIFO); 13 leaves queues for the host framework
     Pool dev, pin;
     bool profiling = false;
     int variant = 0;

@@ -92,6 +92,7 @@ struct ShaTune {
     int thr_x10 = 25;    // PBSGPU_HYBRID_THR_X10: chunks longer than thr_x10/10 x avg take the latency kernel
     int serial = 0;      // PBSGPU_HYBRID_SERIAL: latency kernel on the job's own stream (diagnostic)
     int spread_kb = 30;  // PBSGPU_SPLIT_SPREAD_KB: dummy dynamic shared memory per latency CTA (caps CTAs per SM)
+    int head_per_sm = 32; // PBSGPU_HYBRID_HEAD_PER_SM: chunks per SM of the long partition (and job) that may take the latency kernel
 };
 cudaError_t launch_sha_simple(const ShaArgs &a, cudaStream_t st);
 cudaError_t launch_sha_tuned(const ShaArgs &a, const ShaTune &tune, cudaStream_t st);   // throughput kernel
