@@ -100,10 +100,10 @@ def instr_ceiling(sm_total, sm_mhz, value_gbs):
     """Integer-pipe bound of SHA-256 on this GPU.  Every one of the chip's SMs runs SHA work (124 the bulk kernel, 24
     the long-chunk kernel), so the bound counts ALL of them: 64 ALU-pipe thread-instructions / clk / SM
     (profiles/r01_microbench.txt) over the ALU instructions per byte of the shipped kernel
-    (profiles/r02_sass_mix.txt: loop of k_sha_tuned<2>, 1226 ALU-pipe instructions per 64 B block)."""
+    (profiles/r02_sass_mix.txt: loop of k_sha_tuned<2>, 1228 ALU-pipe instructions per 64 B block)."""
     if not sm_mhz:
         return None
-    alu_per_block = 1226.0
+    alu_per_block = 1228.0
     gbs = sm_total * 64 * float(sm_mhz) * 1e6 / (alu_per_block / 64.0) / 1e9
     return {"alu_pipe_GBps": gbs, "frac_of_alu_pipe": value_gbs / gbs if gbs else None, "sm_count": sm_total,
             "alu_instr_per_64B": alu_per_block,

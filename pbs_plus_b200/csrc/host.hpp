@@ -36,7 +36,7 @@ struct Scoped {
     explicit operator bool() const { return p != nullptr; }
 };
 
-constexpr int N_STREAMS = 15;   // upper bound of stream slots (main + side stream each); 2 x 15 + copy + tail = 32 HW connections
+constexpr int N_STREAMS = 32;   // upper bound of stream slots (main + side stream each); beyond 15 slots streams share the 32 HW queues
 
 struct pbsgpu_job;
 struct pbsgpu_ctx {
