@@ -18,6 +18,8 @@ run base X=1 | tee -a gpurun_out/r2c_sweep.txt
 run slots8 PBSGPU_SLOTS=8 | tee -a gpurun_out/r2c_sweep.txt
 run slots10 PBSGPU_SLOTS=10 | tee -a gpurun_out/r2c_sweep.txt
 run slots15 PBSGPU_SLOTS=15 | tee -a gpurun_out/r2c_sweep.txt
+run slots20 PBSGPU_SLOTS=20 | tee -a gpurun_out/r2c_sweep.txt
+run slots26 PBSGPU_SLOTS=26 | tee -a gpurun_out/r2c_sweep.txt
 run p32_t20_h64 PBSGPU_PARTITION_SMS=32 PBSGPU_HYBRID_THR_X10=20 PBSGPU_HYBRID_HEAD_PER_SM=64 | tee -a gpurun_out/r2c_sweep.txt
 run p40_t15_h96 PBSGPU_PARTITION_SMS=40 PBSGPU_HYBRID_THR_X10=15 PBSGPU_HYBRID_HEAD_PER_SM=96 | tee -a gpurun_out/r2c_sweep.txt
 run p32_t15_h128 PBSGPU_PARTITION_SMS=32 PBSGPU_HYBRID_THR_X10=15 PBSGPU_HYBRID_HEAD_PER_SM=128 | tee -a gpurun_out/r2c_sweep.txt
