@@ -282,7 +282,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 
 // consumer: 64 rounds with W+K supplied.  CMODE 0: IADD3 forms (fewest instructions),
-// CMODE 1: all additions on the FMA pipe (a*1+b with an opaque 1).
+// CMODE 1: all additions on the FMA pipe (a*1+b with an opaque 1),
+// CMODE 2: the two additions on the chain (e', a') stay IADD3, everything that only depends on values known at the
+//          start of the round (h+kw, d+h+kw, h+kw+maj) and the Sigma0 add go to the FMA pipe: 12 ALU + 4 FMA per round.
 template <int CMODE>
 __device__ __forceinline__ void sha_rounds(Sha256State &s, const uint4 (&kwv)[16], const Opq &o) {
     typedef Ops<CMODE ? 1 : 0> P;
@@ -298,7 +300,11 @@ __device__ __forceinline__ void sha_rounds(Sha256State &s, const uint4 (&kwv)[16
         uint32_t S0 = rotr(a, 2) ^ rotr(a, 13) ^ rotr(a, 22);
         uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
         uint32_t en, an;
-        if (CMODE) {
+        if (CMODE == 2) {
+            uint32_t m = P::add(P::add(hk, mj, o), S0, o);
+            en = S1 + ch + dhk;                   // IADD3 (on the e chain)
+            an = S1 + ch + m;                     // IADD3 (on the a chain)
+        } else if (CMODE) {
             uint32_t s1ch = P::add(S1, ch, o);
             en = P::add(s1ch, dhk, o);
             uint32_t x = P::add(P::add(S0, mj, o), hk, o);
@@ -449,6 +455,7 @@ cudaError_t launch_sha_split(const ShaArgs &a, const ShaTune &tune, cudaStream_t
         case 10: return launch_split_t<0, 0>(a, o, blocks, tune.spread_kb, st);
         case 12: return launch_split_t<0, 1>(a, o, blocks, tune.spread_kb, st);
         case 13: return launch_split_t<3, 1>(a, o, blocks, tune.spread_kb, st);
+        case 14: return launch_split_t<3, 2>(a, o, blocks, tune.spread_kb, st);
         default: return launch_split_t<3, 0>(a, o, blocks, tune.spread_kb, st);   // producer balanced, consumer IADD3
     }
 }

@@ -221,6 +221,7 @@ static const Variant VS[] = {
     {"product k_sha_tuned<3>", prod_tuned<3>},
     {"product k_sha_split<3,0>", prod_split<3, 0>},
     {"product k_sha_split<3,1>", prod_split<3, 1>},
+    {"product k_sha_split<3,2>", prod_split<3, 2>},
 };
 static const int NV = (int)(sizeof VS / sizeof VS[0]);
 
@@ -295,18 +296,19 @@ int main(int argc, char **argv) {
         // load curve: C concurrent chains of equal length; time per 64 B block of a chain = the chain latency that bounds
         // a batch's makespan, GB/s = throughput at that load.  C = 148 SMs x 4 sub-partitions x 32 lanes x {1/4 .. 8} warps.
         const uint64_t chain = (argc > 2 ? atoll(argv[2]) : 1024) << 10;   // bytes per chain
-        int picks[6] = {0, 3, 4, -1, -1, -1};                               // v0, v11, v27, then tuned<2>, split<3,0>, split<3,1> by name
+        int picks[7] = {0, 3, 4, -1, -1, -1, -1};                               // v0, v11, v27, then tuned<2>, split<3,0>, split<3,1> by name
         for (int v = 0; v < NV; v++) {
             if (!strcmp(VS[v].name, "product k_sha_tuned<2>")) picks[3] = v;
             if (!strcmp(VS[v].name, "product k_sha_split<3,0>")) picks[4] = v;
             if (!strcmp(VS[v].name, "product k_sha_split<3,1>")) picks[5] = v;
+            if (!strcmp(VS[v].name, "product k_sha_split<3,2>")) picks[6] = v;
         }
         const uint32_t base_c = (uint32_t)sms * 4 * 32;
         const double mult[] = {0.25, 0.5, 1, 2, 4, 8};
         const uint32_t max_n = (uint32_t)(base_c * 8);
         B.init((uint64_t)max_n * chain > (64ull << 30) ? (64ull << 30) : (uint64_t)max_n * chain, max_n);
         printf("chains of %llu KiB; C chains = m x %u (one warp per sub-partition at m = 1)\n", (unsigned long long)(chain >> 10), base_c);
-        for (int pi = 0; pi < 6; pi++) {
+        for (int pi = (argc > 3 ? atoi(argv[3]) : 0); pi < 7; pi++) {
             for (int mi = 0; mi < 6; mi++) {
                 const uint32_t n = (uint32_t)(base_c * mult[mi]);
                 uint64_t len = chain; while ((uint64_t)n * len > B.total) len >>= 1;   // keep within the buffer
