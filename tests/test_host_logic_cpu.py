@@ -121,3 +121,97 @@ def test_verify_backed_file_hashes_mirrors_the_reference_errors(tmp_path):
     (tmp_path / "big").unlink()
     with pytest.raises(IOError, match='open backed file "big" for verification'):
         transfer.verifyBackedFileHashes(eng, opener, hashes)
+
+
+# ---- the layout-faithful writer (host logic only; the real engine runs the same flows in tests/test_gpu_round2.py) ----
+class OracleStream:
+    """Stand-in for engine.Stream: buffers the bytes and the suggested boundaries, answers finish() with the oracle."""
+
+    def __init__(self, cfg, known):
+        self.cfg, self.known, self.buf, self.sug, self.done = cfg, known, bytearray(), [], False
+        self._slot = np.zeros(4096, dtype=np.uint8)
+
+    position = property(lambda self: len(self.buf))
+
+    def write(self, data): self.buf += bytes(np.asarray(data, dtype=np.uint8))
+    def suggest(self, off):
+        assert off >= len(self.buf) and (not self.sug or off > self.sug[-1])
+        self.sug.append(off)
+    def reserve(self): return self._slot
+    def commit(self, n): self.buf += self._slot[:n].tobytes()
+    def poll(self, cap=0): return np.zeros(0, dtype=oracle.CHUNK_DTYPE)
+    def finish(self):
+        data = np.frombuffer(bytes(self.buf), dtype=np.uint8)
+        rec = oracle.chunk_digest_forced(oracle.config(self.cfg.avg), data, np.array([s for s in self.sug if 0 < s < len(data)], np.uint64))
+        if self.known is not None:
+            rec["flags"] = self.known.insert(rec["digest"]) * CHUNK_KNOWN
+        return rec
+    def close(self): self.done = True
+
+
+class OracleStreamEngine(OracleEngine):
+    def stream(self, cfg, known=None):
+        return OracleStream(cfg, known)
+
+
+def _payload_stream(files):
+    parts, pos, starts = [transfer.PXAR_PAYLOAD_START_MARKER.to_bytes(8, "little") + (16).to_bytes(8, "little")], 16, []
+    for f in files:
+        starts.append(pos); parts += [transfer.payload_header(len(f)), f.tobytes()]; pos += 16 + len(f)
+    parts.append(transfer.PXAR_PAYLOAD_TAIL_MARKER.to_bytes(8, "little") + (16).to_bytes(8, "little"))
+    return np.frombuffer(b"".join(parts), dtype=np.uint8), starts
+
+
+def test_payload_header_layout():
+    h = transfer.payload_header(1000)
+    assert len(h) == 16 and int.from_bytes(h[:8], "little") == transfer.PXAR_PAYLOAD and int.from_bytes(h[8:], "little") == 1016
+
+
+def test_payload_stream_writer_frames_entries_and_returns_payload_offsets():
+    eng = OracleStreamEngine()
+    files = [rnd(n, 20 + i) for i, n in enumerate([0, 5, 30_000, 4096, 77_777])]
+    w = transfer.PayloadStreamWriter(eng, buzhash.NewConfigBytes(1024), eng.digest_set())
+    stream, starts = _payload_stream(files)
+    for i, f in enumerate(files):
+        assert w.WriteEntryReader(transfer.Entry(f"f{i}", len(f)), io.BytesIO(f.tobytes()), len(f)) == starts[i]
+    idx = w.Finish()
+    ref = oracle.chunk_digest_forced(oracle.config(1024), stream, np.array(starts, np.uint64))
+    assert [(e, d) for e, d, _ in idx] == [(int(r["end_off"]), bytes(r["digest"])) for r in ref]
+    assert idx[-1][0] == len(stream) and w.payload_offsets == {f"f{i}": s for i, s in enumerate(starts)}
+    with pytest.raises(RuntimeError):
+        w.WriteEntryReader(transfer.Entry("late", 1), io.BytesIO(b"x"), 1)
+    with pytest.raises(IOError, match="unexpected EOF"):
+        transfer.PayloadStreamWriter(eng, buzhash.NewConfigBytes(1024)).WriteEntryReader(transfer.Entry("s", 9), io.BytesIO(b"abc"), 9)
+
+
+def test_write_entry_ref_splices_the_previous_index_and_rejects_descending_offsets():
+    """commit.go:752 / :848-860: chunk reuse by reference; the error text carries "not strictly greater"."""
+    eng = OracleStreamEngine()
+    cfg = buzhash.NewConfigBytes(1024)
+    files = [rnd(n, 60 + i) for i, n in enumerate([40_000, 30_000, 50_000])]
+    w0 = transfer.PayloadStreamWriter(eng, cfg)
+    offs = [w0.WriteEntryReader(transfer.Entry(f"f{i}", len(f)), io.BytesIO(f.tobytes()), len(f)) for i, f in enumerate(files)]
+    prev = w0.Finish()
+    ends = np.array([e for e, _, _ in prev], dtype=np.uint64)
+    digs = np.array([np.frombuffer(d, dtype=np.uint8) for _, d, _ in prev])
+    w1 = transfer.PayloadStreamWriter(eng, cfg, prev_index=(ends, digs))
+    head = rnd(7000, 99)
+    w1.WriteEntryReader(transfer.Entry("new", len(head)), io.BytesIO(head.tobytes()), len(head))
+    pos_before = w1.position
+    o1 = w1.WriteEntryRef(transfer.Entry("f1", len(files[1])), offs[1])
+    lo = int(np.searchsorted(ends, offs[1], side="right"))
+    hi = int(np.searchsorted(ends, offs[1] + 16 + len(files[1]), side="left"))
+    first_start = int(ends[lo - 1]) if lo else 0
+    assert o1 == pos_before + (offs[1] - first_start)                    # same distance from the first injected chunk's start
+    assert w1.position == pos_before + int(ends[hi]) - first_start       # the injected chunks' bytes are part of the new stream
+    with pytest.raises(transfer.NotStrictlyGreater, match="not strictly greater"):
+        w1.WriteEntryRef(transfer.Entry("f0", len(files[0])), offs[0])
+    with pytest.raises(IOError, match="outside the previous index"):
+        w1.WriteEntryRef(transfer.Entry("f2", 10**9), offs[2])
+    idx = w1.Finish()
+    injected = [(d, k) for e, d, k in idx if pos_before < e <= w1.position - 16]
+    assert [d for d, _ in injected][: hi - lo + 1] == [bytes(x) for x in digs[lo: hi + 1]] and all(k for _, k in injected[: hi - lo + 1])
+    e = [x[0] for x in idx]
+    assert e == sorted(e) and len(set(e)) == len(e)
+    with pytest.raises(IOError, match="without a previous payload index"):
+        transfer.PayloadStreamWriter(eng, cfg).WriteEntryRef(transfer.Entry("x", 1), 5)
