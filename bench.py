@@ -470,7 +470,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "l2": "inputs (>= 64 GiB) far exceed the 126 MB L2; no flush needed",
             "pipelining": "K steps submitted asynchronously over the SAME resident batch (13 stream slots, FIFO per slot); all "
                           "complete inside the timed region; see value_distinct for non-repeating data",
-            "inflight": args.inflight or args.steps, "sm_partition(long,bulk)": list(eng.partition_info()),
+            "inflight": args.inflight or args.steps, "sm_partition(long,bulk,scan)": list(eng.partition_info()) + [eng.scan_partition_sms()],
             "known_hit_rate_last_step": hit_last, "first_pass_check": check,
         },
         "clocks": clocks,

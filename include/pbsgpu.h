@@ -97,6 +97,8 @@ int pbsgpu_set_profiling(pbsgpu_ctx *ctx, int on);
 /* SM partition in effect (CUDA green contexts; PBSGPU_PARTITION_SMS=n at open): SMs reserved for the
  * long-chunk latency kernels / SMs for everything else; both 0 when the GPU is not partitioned. */
 int pbsgpu_partition_info(pbsgpu_ctx *ctx, int *long_sms, int *bulk_sms);
+/* SMs that run only the front halves (K1 scan, sort, K2 resolve; PBSGPU_SCAN_SMS=n at open); 0 = they share the bulk SMs. */
+int pbsgpu_scan_partition_sms(pbsgpu_ctx *ctx);
 /* 0 = tuned kernels (default), 1 = simple cross-check kernels (same results) */
 int pbsgpu_set_kernel_variant(pbsgpu_ctx *ctx, int variant);
 

@@ -69,7 +69,7 @@ class Corpus(C.Structure):
 # every symbol include/pbsgpu.h declares (tests assert the .so exports all of them)
 SYMBOLS = [
     "pbsgpu_version", "pbsgpu_open", "pbsgpu_close", "pbsgpu_strerror", "pbsgpu_device_info",
-    "pbsgpu_set_profiling", "pbsgpu_partition_info", "pbsgpu_set_kernel_variant", "pbsgpu_config", "pbsgpu_config_kib",
+    "pbsgpu_set_profiling", "pbsgpu_partition_info", "pbsgpu_scan_partition_sms", "pbsgpu_set_kernel_variant", "pbsgpu_config", "pbsgpu_config_kib",
     "pbsgpu_default_table", "pbsgpu_chunk_digest_batch", "pbsgpu_batch_submit", "pbsgpu_batch_wait",
     "pbsgpu_chunk_digest_batch_ex", "pbsgpu_batch_submit_ex", "pbsgpu_batch_free",
     "pbsgpu_scan_batch", "pbsgpu_sha256_batch", "pbsgpu_stream_open", "pbsgpu_stream_write",
@@ -106,6 +106,7 @@ def lib() -> C.CDLL:
     L.pbsgpu_device_info.argtypes = [vp, C.POINTER(DevInfo)]
     L.pbsgpu_set_profiling.argtypes = [vp, C.c_int]
     L.pbsgpu_partition_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.pbsgpu_scan_partition_sms.argtypes = [vp]
     L.pbsgpu_set_kernel_variant.argtypes = [vp, C.c_int]
     L.pbsgpu_config.argtypes = [C.c_uint32, u32p, C.POINTER(Cfg)]
     L.pbsgpu_config_kib.argtypes = [C.c_uint32, u32p, C.POINTER(Cfg)]

@@ -103,41 +103,61 @@ bool pbsgpu_cfg_ok(const pbsgpu_cfg *c) {
 // not link libcuda): long-chunk latency kernels get `want` SMs of their own, so they are neither
 // slowed by co-resident bulk warps nor packed onto a few SMs.  Returns false when the driver does not
 // offer it; streams created before a failure are destroyed by ctx_destroy (streams_made stays false).
-static bool make_partition(pbsgpu_ctx *ctx, int want) {
+static bool make_partition(pbsgpu_ctx *ctx, int want, int want_scan) {
     auto devget = pbsgpu_driver_ep<CUresult (*)(CUdevice *, int)>("cuDeviceGet");
     auto getRes = pbsgpu_driver_ep<CUresult (*)(CUdevice, CUdevResource *, CUdevResourceType)>("cuDeviceGetDevResource");
     auto split = pbsgpu_driver_ep<CUresult (*)(CUdevResource *, unsigned *, const CUdevResource *, CUdevResource *, unsigned, unsigned)>("cuDevSmResourceSplitByCount");
     auto genDesc = pbsgpu_driver_ep<CUresult (*)(CUdevResourceDesc *, CUdevResource *, unsigned)>("cuDevResourceGenerateDesc");
     auto gcreate = pbsgpu_driver_ep<CUresult (*)(CUgreenCtx *, CUdevResourceDesc, CUdevice, unsigned)>("cuGreenCtxCreate");
     auto gstream = pbsgpu_driver_ep<CUresult (*)(CUstream *, CUgreenCtx, unsigned, int)>("cuGreenCtxStreamCreate");
+    auto gdestroy = pbsgpu_driver_ep<CUresult (*)(CUgreenCtx)>("cuGreenCtxDestroy");
     if (!devget || !getRes || !split || !genDesc || !gcreate || !gstream) return false;
     cudaFree(0);   // make sure the primary context exists
     CUdevice dev;
-    CUdevResource all, grp[1], rest;
+    CUdevResource all, grp[1], rest, sgrp[1], rest2;
     unsigned n = 1;
-    CUdevResourceDesc dA, dB;
+    CUdevResourceDesc dA, dB, dC;
     if (devget(&dev, ctx->device) != CUDA_SUCCESS || getRes(dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return false;
     if (split(grp, &n, &all, &rest, 0, (unsigned)want) != CUDA_SUCCESS || n < 1 || rest.sm.smCount == 0) return false;
-    if (genDesc(&dA, &grp[0], 1) != CUDA_SUCCESS || genDesc(&dB, &rest, 1) != CUDA_SUCCESS) return false;
-    if (gcreate(&ctx->g_long, dA, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return false;
-    if (gcreate(&ctx->g_bulk, dB, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return false;
-    cudaStream_t a[N_STREAMS] = {}, b[N_STREAMS] = {};
-    bool ok = true;
+    bool three = false;
+    if (want_scan > 0 && (unsigned)want_scan + 8 <= rest.sm.smCount) {
+        n = 1;
+        three = split(sgrp, &n, &rest, &rest2, 0, (unsigned)want_scan) == CUDA_SUCCESS && n >= 1 && rest2.sm.smCount > 0;
+    }
+    CUdevResource &bulk = three ? rest2 : rest;
+    CUgreenCtx gl = nullptr, gb = nullptr, gs = nullptr;
+    bool ok = genDesc(&dA, &grp[0], 1) == CUDA_SUCCESS && genDesc(&dB, &bulk, 1) == CUDA_SUCCESS &&
+              (!three || genDesc(&dC, &sgrp[0], 1) == CUDA_SUCCESS);
+    ok = ok && gcreate(&gl, dA, dev, CU_GREEN_CTX_DEFAULT_STREAM) == CUDA_SUCCESS;
+    ok = ok && gcreate(&gb, dB, dev, CU_GREEN_CTX_DEFAULT_STREAM) == CUDA_SUCCESS;
+    ok = ok && (!three || gcreate(&gs, dC, dev, CU_GREEN_CTX_DEFAULT_STREAM) == CUDA_SUCCESS);
+    cudaStream_t a[N_STREAMS] = {}, b[N_STREAMS] = {}, c[N_SCAN_STREAMS] = {};
     for (int i = 0; i < ctx->n_slots && ok; i++) {
         CUstream sa = nullptr, sb = nullptr;
-        ok = gstream(&sb, ctx->g_bulk, CU_STREAM_NON_BLOCKING, 0) == CUDA_SUCCESS;
+        ok = gstream(&sb, gb, CU_STREAM_NON_BLOCKING, 0) == CUDA_SUCCESS;
         if (ok) b[i] = (cudaStream_t)sb;
-        ok = ok && gstream(&sa, ctx->g_long, CU_STREAM_NON_BLOCKING, 0) == CUDA_SUCCESS;
+        ok = ok && gstream(&sa, gl, CU_STREAM_NON_BLOCKING, 0) == CUDA_SUCCESS;
         if (ok) a[i] = (cudaStream_t)sa;
+    }
+    for (int i = 0; i < N_SCAN_STREAMS && ok && three; i++) {
+        CUstream sc = nullptr;
+        ok = gstream(&sc, gs, CU_STREAM_NON_BLOCKING, 0) == CUDA_SUCCESS;
+        if (ok) c[i] = (cudaStream_t)sc;
     }
     if (!ok) {   // half-made: nothing of it reaches the context
         for (int i = 0; i < N_STREAMS; i++) { if (a[i]) cudaStreamDestroy(a[i]); if (b[i]) cudaStreamDestroy(b[i]); }
+        for (int i = 0; i < N_SCAN_STREAMS; i++) if (c[i]) cudaStreamDestroy(c[i]);
+        if (gdestroy) { if (gl) gdestroy(gl); if (gb) gdestroy(gb); if (gs) gdestroy(gs); }
+        (void)cudaGetLastError();
         return false;
     }
     for (int i = 0; i < N_STREAMS; i++) { ctx->streams[i] = b[i]; ctx->streams2[i] = a[i]; }
+    for (int i = 0; i < N_SCAN_STREAMS; i++) ctx->scan_streams[i] = c[i];
+    ctx->g_long = gl; ctx->g_bulk = gb; ctx->g_scan = gs;
     ctx->part_sms = (int)grp[0].sm.smCount;
-    ctx->bulk_sms = (int)rest.sm.smCount;
-    ctx->sm_count = ctx->bulk_sms;   // persistent kernels (scan) size their grid to the bulk partition
+    ctx->bulk_sms = (int)bulk.sm.smCount;
+    ctx->scan_sms = three ? (int)sgrp[0].sm.smCount : 0;
+    ctx->sm_count = ctx->bulk_sms;   // persistent kernels on the bulk streams (CRC-32, ...) size their grid to the bulk partition
     return true;
 }
 
@@ -149,6 +169,7 @@ static void ctx_destroy(pbsgpu_ctx *ctx) {
         if (ctx->streams[i]) cudaStreamDestroy(ctx->streams[i]);
         if (ctx->streams2[i]) cudaStreamDestroy(ctx->streams2[i]);
     }
+    for (int i = 0; i < N_SCAN_STREAMS; i++) if (ctx->scan_streams[i]) cudaStreamDestroy(ctx->scan_streams[i]);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->tail_stream) cudaStreamDestroy(ctx->tail_stream);
     if (ctx->d_table) cudaFree(ctx->d_table);
@@ -156,9 +177,9 @@ static void ctx_destroy(pbsgpu_ctx *ctx) {
     if (ctx->d_crc_tables) cudaFree(ctx->d_crc_tables);
     if (ctx->d_xxh_tab) cudaFree(ctx->d_xxh_tab);
     if (ctx->epoch) cudaEventDestroy(ctx->epoch);
-    if (ctx->g_long || ctx->g_bulk) {
+    if (ctx->g_long || ctx->g_bulk || ctx->g_scan) {
         auto gdestroy = pbsgpu_driver_ep<CUresult (*)(CUgreenCtx)>("cuGreenCtxDestroy");
-        if (gdestroy) { if (ctx->g_long) gdestroy(ctx->g_long); if (ctx->g_bulk) gdestroy(ctx->g_bulk); }
+        if (gdestroy) { if (ctx->g_long) gdestroy(ctx->g_long); if (ctx->g_bulk) gdestroy(ctx->g_bulk); if (ctx->g_scan) gdestroy(ctx->g_scan); }
     }
     ctx->dev.destroy(); ctx->pin.destroy();
     (void)cudaGetLastError();
@@ -207,7 +228,9 @@ extern "C" int pbsgpu_open(int device, pbsgpu_ctx **out) {
         const int side_prio = env_int("PBSGPU_HYBRID_PRIO", 0) ? prio_hi : prio_lo;   // 1: long-chunk kernels on a high-priority stream
         // default: 24 SMs reserved for the long-chunk latency kernels (green contexts); 0 disables
         const int want_part = env_int("PBSGPU_PARTITION_SMS", 24);
-        const bool partitioned = want_part > 0 && want_part + 8 <= ctx->sm_count && make_partition(ctx, want_part);
+        // + PBSGPU_SCAN_SMS (default 24) SMs that run only the front halves (K1 scan / sort / K2); 0 = scans share the bulk partition
+        const int want_scan = env_int("PBSGPU_SCAN_SMS", 24);
+        const bool partitioned = want_part > 0 && want_part + 8 <= ctx->sm_count && make_partition(ctx, want_part, want_scan);
         bool ok = true;
         for (int i = 0; i < ctx->n_slots && !partitioned && ok; i++)
             ok = cudaStreamCreateWithFlags(&ctx->streams[i], cudaStreamNonBlocking) == cudaSuccess &&
@@ -257,6 +280,7 @@ extern "C" int pbsgpu_partition_info(pbsgpu_ctx *ctx, int *long_sms, int *bulk_s
     if (bulk_sms) *bulk_sms = ctx->bulk_sms;
     return PBSGPU_OK;
 }
+extern "C" int pbsgpu_scan_partition_sms(pbsgpu_ctx *ctx) { return ctx ? ctx->scan_sms : 0; }
 extern "C" int pbsgpu_set_profiling(pbsgpu_ctx *ctx, int on) { if (!ctx) return PBSGPU_EINVAL; ctx->profiling = on != 0; return 0; }
 extern "C" int pbsgpu_set_kernel_variant(pbsgpu_ctx *ctx, int v) { if (!ctx || v < 0 || v > 1) return PBSGPU_EINVAL; ctx->variant = v; return 0; }
 
@@ -284,12 +308,22 @@ static int upload_table(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg, cudaStream_t st)
 // ---------------------------------------------------------------------------
 // Job: one batch of device-resident streams through K1..K4 on one CUDA stream.
 // ---------------------------------------------------------------------------
+cudaError_t pbsgpu_job_sync(pbsgpu_job *j) {   // everything the job enqueued, on all of its streams
+    cudaError_t e = cudaSuccess, r;
+    if (j->ss && j->ss != j->st && (r = cudaStreamSynchronize(j->ss)) != cudaSuccess) e = r;
+    if (j->st && (r = cudaStreamSynchronize(j->st)) != cudaSuccess) e = r;
+    if (j->st2 && (r = cudaStreamSynchronize(j->st2)) != cudaSuccess) e = r;
+    if (j->enqueued && j->have_events && (r = cudaEventSynchronize(j->ev[EV_END])) != cudaSuccess) e = r;
+    if (e != cudaSuccess) (void)cudaGetLastError();
+    return e;
+}
+
 void pbsgpu_job_release(pbsgpu_job *j) {
     if (!j) return;
     pbsgpu_ctx *c = j->ctx;
     if (j->enqueued && j->have_events) { cudaEventSynchronize(j->ev[EV_END]); (void)cudaGetLastError(); }   // the tail may run on the tail stream
     if (j->set && j->enqueued && !j->reconciled) {   // abandoned after its probe was enqueued: settle the set's bookkeeping
-        cudaStreamSynchronize(j->st);
+        pbsgpu_job_sync(j);
         pbsgpu_set_reconcile(j->set, j->chunk_cap, j->h_counters ? j->h_counters[3] : 0);
         j->reconciled = true;
     }
@@ -415,6 +449,8 @@ int pbsgpu_job_create(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg, const void *base_d
     j->st = ctx->streams[ctx->next_stream];
     j->st2 = ctx->streams2[ctx->next_stream];
     ctx->next_stream = (ctx->next_stream + 1) % ctx->n_slots;
+    if (ctx->scan_sms > 0) { j->ss = ctx->scan_streams[ctx->next_scan]; ctx->next_scan = (ctx->next_scan + 1) % N_SCAN_STREAMS; }
+    else j->ss = j->st;
     int rc = job_alloc(j);
     if (rc) { pbsgpu_job_release(j); return rc; }
     for (int i = 0; i < EV_COUNT; i++)
@@ -439,7 +475,7 @@ static bool hybrid_for(const pbsgpu_ctx *ctx) {
 // front half: inputs -> K1 scan -> sort -> K2 resolve (chunk list known on the device afterwards)
 int pbsgpu_job_enqueue_front(pbsgpu_job *j) {
     pbsgpu_ctx *ctx = j->ctx;
-    cudaStream_t st = j->st;
+    cudaStream_t st = j->ss;   // the scan partition's stream (= the job's own stream when the GPU has no scan partition)
     const uint32_t n = j->n;
     int rc = upload_table(ctx, &j->cfg, st);
     if (rc) return rc;
@@ -461,9 +497,9 @@ int pbsgpu_job_enqueue_front(pbsgpu_job *j) {
     else if (j->scan_lanes) {
         uint64_t extent = 0;
         for (uint32_t i = 0; i < n; i++) extent = std::max(extent, j->off[i] + j->len[i]);
-        CK(launch_scan_lanes(sa, ctx->d_rot, ctx->sm_count, extent, st));
+        CK(launch_scan_lanes(sa, ctx->d_rot, ctx->scan_sms > 0 ? ctx->scan_sms : ctx->sm_count, extent, st));
     }
-    else CK(launch_scan_tuned(sa, ctx->d_rot, ctx->sm_count, st));
+    else CK(launch_scan_tuned(sa, ctx->d_rot, ctx->scan_sms > 0 ? ctx->scan_sms : ctx->sm_count, st));
     if (j->d_forced) CK(launch_append_keys(j->d_forced, j->forced_keys.size(), j->d_cand, j->cand_cap, &j->d_counters[0], st));
     CK(cudaEventRecord(j->ev[EV_SCAN], st));
     // candidates -> sorted by (stream, position)
@@ -477,7 +513,7 @@ int pbsgpu_job_enqueue_front(pbsgpu_job *j) {
     ra.chunk_first = j->d_chunk_first; ra.chunks = j->d_chunks; ra.chunk_cap = j->chunk_cap; ra.consumed = j->d_consumed;
     ra.n_chunks = &j->d_counters[1];
     CK(launch_resolve(ra, st));
-    if (j->profiling) CK(cudaEventRecord(j->ev[EV_RESOLVE], st));
+    CK(cudaEventRecord(j->ev[EV_RESOLVE], st));
     j->front_done = true;
     j->back_done = false;
     return PBSGPU_OK;
@@ -489,6 +525,7 @@ int pbsgpu_job_enqueue_back(pbsgpu_job *j) {
     cudaStream_t st = j->st;
     const uint32_t n = j->n;
     size_t tb = j->temp_bytes;
+    if (j->ss != st) CK(cudaStreamWaitEvent(st, j->ev[EV_RESOLVE], 0));   // the chunk list comes from the scan partition
     if (j->profiling) CK(cudaEventRecord(j->ev[EV_BACK], st));
     if (j->want_digests && j->chunk_cap) {
         CK(launch_len_keys(j->d_chunks, &j->d_counters[1], j->chunk_cap, j->d_keys, j->d_vals, st));
@@ -632,7 +669,7 @@ extern "C" int pbsgpu_batch_submit_ex(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg, co
     rc = pbsgpu_job_create(ctx, cfg, base_dev, off, len, n, 1, 1, o.set, o.forced_stream, o.forced_off, o.n_forced, &j);
     if (rc) return rc;
     rc = pbsgpu_job_enqueue(j);
-    if (rc) { cudaStreamSynchronize(j->st); pbsgpu_job_release(j); return rc; }
+    if (rc) { pbsgpu_job_sync(j); pbsgpu_job_release(j); return rc; }
     *job = j;
     return PBSGPU_OK;
 }
@@ -654,7 +691,7 @@ extern "C" int pbsgpu_batch_wait(pbsgpu_job *j, pbsgpu_chunk *out, uint64_t cap,
             return fail(ctx, PBSGPU_ERANGE, "output capacity %llu < %llu chunks", (unsigned long long)cap, (unsigned long long)nch);
         if (nch) memcpy(out, j->h_out, nch * sizeof(pbsgpu_chunk));
     } else {
-        cudaStreamSynchronize(j->st);
+        pbsgpu_job_sync(j);
     }
     pbsgpu_job_release(j);
     return rc;
@@ -663,8 +700,7 @@ extern "C" int pbsgpu_batch_wait(pbsgpu_job *j, pbsgpu_chunk *out, uint64_t cap,
 extern "C" void pbsgpu_batch_free(pbsgpu_job *j) {
     if (!j) return;
     Guard g(j->ctx);
-    cudaStreamSynchronize(j->st);
-    cudaStreamSynchronize(j->st2);
+    pbsgpu_job_sync(j);
     pbsgpu_job_release(j);
 }
 
@@ -736,7 +772,7 @@ static int batch_host(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg, const uint8_t *bas
                 }
             }
             produced += nch;
-        } else cudaStreamSynchronize(j->st);
+        } else pbsgpu_job_sync(j);
         pbsgpu_job_release(j);
         jobs[gi] = nullptr;
         return r;
@@ -765,10 +801,10 @@ static int batch_host(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg, const uint8_t *bas
         rc = pbsgpu_job_create(ctx, cfg, buf, goff.data(), glen.data(), g.count, 1, 1, o.set, fs.data(), o.forced_off + g.f_lo,
                                g.f_hi - g.f_lo, &j);
         if (rc) break;
-        cudaStreamWaitEvent(j->st, copied[gi], 0);
+        cudaStreamWaitEvent(j->ss, copied[gi], 0);
         rc = pbsgpu_job_enqueue(j);
         if (rc == PBSGPU_OK && o.stream_xxh3) rc = pbsgpu_xxh3_enqueue(ctx, buf, goff.data(), glen.data(), g.count, j->st, &xruns[gi]);
-        if (rc) { cudaStreamSynchronize(j->st); pbsgpu_job_release(j); break; }
+        if (rc) { pbsgpu_job_sync(j); pbsgpu_job_release(j); break; }
         jobs[gi] = j;
     }
     for (size_t gi = 0; gi < groups.size(); gi++)
@@ -805,7 +841,7 @@ extern "C" int pbsgpu_chunk_digest_batch_ex(pbsgpu_ctx *ctx, const pbsgpu_cfg *c
             produced = j->h_counters[1];
             if (produced > cap) rc = fail(ctx, PBSGPU_ERANGE, "output capacity %llu < %llu chunks", (unsigned long long)cap, (unsigned long long)produced);
             else if (produced) memcpy(out, j->h_out, produced * sizeof(pbsgpu_chunk));
-        } else cudaStreamSynchronize(j->st);
+        } else pbsgpu_job_sync(j);
         if (o.stream_xxh3) { int rx = pbsgpu_xxh3_collect(ctx, &xr, o.stream_xxh3, j->st); if (rc == PBSGPU_OK) rc = rx; }
         pbsgpu_job_release(j);
     } else {
@@ -855,7 +891,7 @@ extern "C" int pbsgpu_scan_batch(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg, const v
                 memcpy(stream_first, first.data(), (n + 1) * 8);
             }
         }
-    } else cudaStreamSynchronize(j->st);
+    } else pbsgpu_job_sync(j);
     pbsgpu_job_release(j);
     return rc;
 }

@@ -86,7 +86,7 @@ static int stream_collect(pbsgpu_stream *s, bool block) {
             if (q == cudaErrorNotReady) { (void)cudaGetLastError(); break; }
         }
         int rc = pbsgpu_job_finish(sj.j);
-        if (rc != PBSGPU_OK) cudaStreamSynchronize(sj.j->st);
+        if (rc != PBSGPU_OK) pbsgpu_job_sync(sj.j);
         s->inflight.pop_front();
         s->busy[sj.buf] = 0;
         if (rc != PBSGPU_OK) { pbsgpu_job_release(sj.j); return rc; }
@@ -116,7 +116,7 @@ static int stream_process(pbsgpu_stream *s, int eof) {
     pbsgpu_job *j = nullptr;
     int rc = pbsgpu_job_create(ctx, &s->cfg, s->buf[s->cur], &off0, &len0, 1, eof, 1, s->set, fstream.data(), foff.data(), foff.size(), &j);
     if (rc) return rc;
-    CK(cudaStreamWaitEvent(j->st, s->copied, 0));       // every byte of the window has arrived before K1 reads it
+    CK(cudaStreamWaitEvent(j->ss, s->copied, 0));       // every byte of the window has arrived before K1 reads it
     // front half now: the cut points decide what has to be carried over
     unsigned long long *counters = j->h_counters;       // pinned
     uint64_t *consumed_p = j->h_consumed;
@@ -124,12 +124,12 @@ static int stream_process(pbsgpu_stream *s, int eof) {
     for (;;) {
         rc = pbsgpu_job_enqueue_front(j);
         if (rc == PBSGPU_OK) {
-            cudaError_t e = cudaMemcpyAsync(counters, j->d_counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, j->st);
-            if (e == cudaSuccess && !eof) e = cudaMemcpyAsync(consumed_p, j->d_consumed, 8, cudaMemcpyDeviceToHost, j->st);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(j->st);
+            cudaError_t e = cudaMemcpyAsync(counters, j->d_counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, j->ss);
+            if (e == cudaSuccess && !eof) e = cudaMemcpyAsync(consumed_p, j->d_consumed, 8, cudaMemcpyDeviceToHost, j->ss);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(j->ss);
             if (e != cudaSuccess) { (void)cudaGetLastError(); rc = fail(ctx, PBSGPU_ECUDA, "stream window: %s", cudaGetErrorString(e)); }
         }
-        if (rc != PBSGPU_OK) { cudaStreamSynchronize(j->st); pbsgpu_job_release(j); return rc; }
+        if (rc != PBSGPU_OK) { pbsgpu_job_sync(j); pbsgpu_job_release(j); return rc; }
         if (counters[0] <= j->cand_cap) break;
         rc = pbsgpu_job_grow_cands(j, counters[0]);          // dense candidates: redo the front half with room for all
         if (rc) { pbsgpu_job_release(j); return rc; }
@@ -146,20 +146,20 @@ static int stream_process(pbsgpu_stream *s, int eof) {
         StreamJob oldest = s->inflight.front();
         cudaEventSynchronize(oldest.j->ev[EV_END]);
         rc = stream_collect(s, false);
-        if (rc) { cudaStreamSynchronize(j->st); pbsgpu_job_release(j); return rc; }
+        if (rc) { pbsgpu_job_sync(j); pbsgpu_job_release(j); return rc; }
     }
-    if (next < 0) { cudaStreamSynchronize(j->st); pbsgpu_job_release(j); return fail(ctx, PBSGPU_ESTATE, "internal: no free stream buffer"); }
+    if (next < 0) { pbsgpu_job_sync(j); pbsgpu_job_release(j); return fail(ctx, PBSGPU_ESTATE, "internal: no free stream buffer"); }
     if (!s->buf[next]) {
         s->buf[next] = (uint8_t *)ctx->dev.get(s->cap);
-        if (!s->buf[next]) { cudaStreamSynchronize(j->st); pbsgpu_job_release(j); return fail(ctx, PBSGPU_ENOMEM, "stream buffer of %llu bytes failed", (unsigned long long)s->cap); }
+        if (!s->buf[next]) { pbsgpu_job_sync(j); pbsgpu_job_release(j); return fail(ctx, PBSGPU_ENOMEM, "stream buffer of %llu bytes failed", (unsigned long long)s->cap); }
     }
     if (rest) {   // carry: ordered on the copy stream in front of the next window's H2D copies, no host wait
         cudaError_t e = cudaMemcpyAsync(s->buf[next], s->buf[s->cur] + consumed, rest, cudaMemcpyDeviceToDevice, ctx->copy_stream);
         if (e == cudaSuccess) e = cudaEventRecord(s->copied, ctx->copy_stream);
-        if (e != cudaSuccess) { (void)cudaGetLastError(); cudaStreamSynchronize(j->st); pbsgpu_job_release(j); return fail(ctx, PBSGPU_ECUDA, "carry copy: %s", cudaGetErrorString(e)); }
+        if (e != cudaSuccess) { (void)cudaGetLastError(); pbsgpu_job_sync(j); pbsgpu_job_release(j); return fail(ctx, PBSGPU_ECUDA, "carry copy: %s", cudaGetErrorString(e)); }
     }
     rc = pbsgpu_job_enqueue_back(j);                          // SHA-256 etc. run while the next window fills
-    if (rc != PBSGPU_OK) { cudaStreamSynchronize(j->st); pbsgpu_job_release(j); return rc; }
+    if (rc != PBSGPU_OK) { pbsgpu_job_sync(j); pbsgpu_job_release(j); return rc; }
     s->busy[s->cur] = 1;
     s->inflight.push_back(StreamJob{j, s->cur, s->base_off});
     s->cur = next; s->fill = rest; s->base_off += consumed;
@@ -305,7 +305,7 @@ extern "C" void pbsgpu_stream_close(pbsgpu_stream *s) {
     pbsgpu_ctx *ctx = s->ctx;
     Guard g(ctx);
     cudaStreamSynchronize(ctx->copy_stream);
-    for (auto &sj : s->inflight) { cudaEventSynchronize(sj.j->ev[EV_END]); cudaStreamSynchronize(sj.j->st); cudaStreamSynchronize(sj.j->st2); pbsgpu_job_release(sj.j); }
+    for (auto &sj : s->inflight) { cudaEventSynchronize(sj.j->ev[EV_END]); pbsgpu_job_sync(sj.j); pbsgpu_job_release(sj.j); }
     for (auto b : s->buf) ctx->dev.put(b);
     if (s->ring) ctx->pin.put(s->ring);
     for (auto e : s->slot_done) if (e) cudaEventDestroy(e);

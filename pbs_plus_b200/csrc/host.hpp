@@ -36,6 +36,7 @@ struct Scoped {
     explicit operator bool() const { return p != nullptr; }
 };
 
+constexpr int N_SCAN_STREAMS = 3;
 constexpr int N_STREAMS = 32;   // upper bound of stream slots (main + side stream each); beyond 15 slots streams share the 32 HW queues
 
 struct pbsgpu_job;
@@ -48,6 +49,8 @@ struct pbsgpu_ctx {
     std::recursive_mutex mu;
     cudaStream_t streams[N_STREAMS] = {};
     cudaStream_t streams2[N_STREAMS] = {};   // forked side stream per job stream (latency kernel of the hybrid SHA launch)
+    cudaStream_t scan_streams[N_SCAN_STREAMS] = {};   // front halves (K1 scan, sort, K2 resolve) in submission order on the scan partition
+    int next_scan = 0;
     cudaStream_t copy_stream = nullptr;
     cudaStream_t tail_stream = nullptr;     // K4 (fused probe) + pack + D2H of every job, in submission order
     bool streams_made = false;
@@ -66,8 +69,11 @@ struct pbsgpu_ctx {
     cudaEvent_t epoch = nullptr;   // recorded at open; kernel intervals are reported relative to it
     // optional spatial partition (CUDA green contexts): `part_sms` SMs are reserved for the latency
     // kernels of long chunks (streams2), everything else runs on the remaining SMs (streams)
-    int part_sms = 0, bulk_sms = 0;
-    CUgreenCtx g_long = nullptr, g_bulk = nullptr;
+    // Round 2: a THIRD partition runs only the front halves (K1 is a whole-SM persistent kernel -- 207 KB of shared memory,
+    // 49 k registers per CTA -- that cannot be placed on an SM holding SHA blocks; sharing SMs with K3 it starved for
+    // up to 1.2 s behind resident SHA blocks, profiles/r02_partition3.txt)
+    int part_sms = 0, bulk_sms = 0, scan_sms = 0;
+    CUgreenCtx g_long = nullptr, g_bulk = nullptr, g_scan = nullptr;
     // knobs, read from the environment ONCE PER CONTEXT in pbsgpu_open (never process-wide statics)
     uint64_t stage_bytes = 0;                 // PBSGPU_STAGE_BYTES: host-input staging group size (0 = auto)
     bool scan_lanes = false;                  // PBSGPU_SCAN_LANES
@@ -133,7 +139,7 @@ enum { EV_START, EV_SCAN, EV_SORT, EV_RESOLVE, EV_SHA, EV_END, EV_FORK, EV_JOIN,
 
 struct pbsgpu_job {
     pbsgpu_ctx *ctx = nullptr;
-    cudaStream_t st = nullptr, st2 = nullptr;
+    cudaStream_t st = nullptr, st2 = nullptr, ss = nullptr;   // back half / long-chunk kernel / front half
     pbsgpu_cfg cfg;
     const uint8_t *base = nullptr;
     std::vector<uint64_t> off, len, tile_first, forced_keys;   // forced_keys: (stream << 40 | offset-1) suggested boundaries
@@ -170,6 +176,7 @@ int pbsgpu_job_enqueue_back(pbsgpu_job *j);
 int pbsgpu_job_enqueue(pbsgpu_job *j);
 int pbsgpu_job_grow_cands(pbsgpu_job *j, unsigned long long nc);
 int pbsgpu_job_finish(pbsgpu_job *j);     // blocks; reruns on candidate overflow; fills ctx->last_timing
+cudaError_t pbsgpu_job_sync(pbsgpu_job *j);
 void pbsgpu_job_release(pbsgpu_job *j);   // waits for nothing: call only after finish or after synchronising j->st
 
 // K7 (capi_aux.cu): enqueue-only / collect pair so the fused batch call can put it on a job's stream

@@ -96,6 +96,10 @@ class Engine:
         self._ck(self._L.pbsgpu_partition_info(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def scan_partition_sms(self) -> int:
+        """SMs reserved for the front halves (K1 scan / sort / K2 resolve); 0 = shared with the bulk partition."""
+        return int(self._L.pbsgpu_scan_partition_sms(self._h))
+
     def set_profiling(self, on: bool):
         self._ck(self._L.pbsgpu_set_profiling(self._h, 1 if on else 0))
 

@@ -440,7 +440,9 @@ def test_empty_batch_and_many_tiny_streams(eng, torch):
 def test_partition_info_is_consistent(eng):
     long_sms, bulk_sms = eng.partition_info()
     total = eng.device_info()["sm_count"]
-    assert (long_sms, bulk_sms) == (0, 0) or (long_sms >= 8 and long_sms + bulk_sms <= 148 and bulk_sms == total)
+    scan_sms = eng.scan_partition_sms()
+    assert (long_sms, bulk_sms) == (0, 0) or (long_sms >= 8 and long_sms + bulk_sms + scan_sms <= 148 and bulk_sms == total)
+    assert scan_sms == 0 or scan_sms >= 8
 
 
 def test_all_long_chunks_take_the_latency_kernel(eng, torch):
