@@ -103,62 +103,108 @@ bool pbsgpu_cfg_ok(const pbsgpu_cfg *c) {
 // not link libcuda): long-chunk latency kernels get `want` SMs of their own, so they are neither
 // slowed by co-resident bulk warps nor packed onto a few SMs.  Returns false when the driver does not
 // offer it; streams created before a failure are destroyed by ctx_destroy (streams_made stays false).
-static bool make_partition(pbsgpu_ctx *ctx, int want, int want_scan) {
-    auto devget = pbsgpu_driver_ep<CUresult (*)(CUdevice *, int)>("cuDeviceGet");
-    auto getRes = pbsgpu_driver_ep<CUresult (*)(CUdevice, CUdevResource *, CUdevResourceType)>("cuDeviceGetDevResource");
-    auto split = pbsgpu_driver_ep<CUresult (*)(CUdevResource *, unsigned *, const CUdevResource *, CUdevResource *, unsigned, unsigned)>("cuDevSmResourceSplitByCount");
-    auto genDesc = pbsgpu_driver_ep<CUresult (*)(CUdevResourceDesc *, CUdevResource *, unsigned)>("cuDevResourceGenerateDesc");
-    auto gcreate = pbsgpu_driver_ep<CUresult (*)(CUgreenCtx *, CUdevResourceDesc, CUdevice, unsigned)>("cuGreenCtxCreate");
-    auto gstream = pbsgpu_driver_ep<CUresult (*)(CUstream *, CUgreenCtx, unsigned, int)>("cuGreenCtxStreamCreate");
-    auto gdestroy = pbsgpu_driver_ep<CUresult (*)(CUgreenCtx)>("cuGreenCtxDestroy");
-    if (!devget || !getRes || !split || !genDesc || !gcreate || !gstream) return false;
-    cudaFree(0);   // make sure the primary context exists
-    CUdevice dev;
-    CUdevResource all, grp[1], rest, sgrp[1], rest2;
-    unsigned n = 1;
+struct GreenApi {
+    CUresult (*devget)(CUdevice *, int);
+    CUresult (*getRes)(CUdevice, CUdevResource *, CUdevResourceType);
+    CUresult (*split)(CUdevResource *, unsigned *, const CUdevResource *, CUdevResource *, unsigned, unsigned);
+    CUresult (*genDesc)(CUdevResourceDesc *, CUdevResource *, unsigned);
+    CUresult (*gcreate)(CUgreenCtx *, CUdevResourceDesc, CUdevice, unsigned);
+    CUresult (*gstream)(CUstream *, CUgreenCtx, unsigned, int);
+    CUresult (*gdestroy)(CUgreenCtx);
+    bool ok() const { return devget && getRes && split && genDesc && gcreate && gstream; }
+};
+static GreenApi green_api() {
+    GreenApi g;
+    g.devget = pbsgpu_driver_ep<decltype(g.devget)>("cuDeviceGet");
+    g.getRes = pbsgpu_driver_ep<decltype(g.getRes)>("cuDeviceGetDevResource");
+    g.split = pbsgpu_driver_ep<decltype(g.split)>("cuDevSmResourceSplitByCount");
+    g.genDesc = pbsgpu_driver_ep<decltype(g.genDesc)>("cuDevResourceGenerateDesc");
+    g.gcreate = pbsgpu_driver_ep<decltype(g.gcreate)>("cuGreenCtxCreate");
+    g.gstream = pbsgpu_driver_ep<decltype(g.gstream)>("cuGreenCtxStreamCreate");
+    g.gdestroy = pbsgpu_driver_ep<decltype(g.gdestroy)>("cuGreenCtxDestroy");
+    return g;
+}
+
+// Builds the green contexts + streams for (long, scan, bulk) = (res_long, res_scan (may be empty), res_bulk); nothing
+// reaches the context unless everything succeeded.
+static bool adopt_partition(pbsgpu_ctx *ctx, const GreenApi &G, CUdevice dev, std::vector<CUdevResource> res_long,
+                            std::vector<CUdevResource> res_scan, std::vector<CUdevResource> res_bulk) {
+    auto count = [](const std::vector<CUdevResource> &v) { unsigned c = 0; for (auto &r : v) c += r.sm.smCount; return c; };
+    if (res_long.empty() || res_bulk.empty() || count(res_long) == 0 || count(res_bulk) == 0) return false;
+    const bool three = !res_scan.empty() && count(res_scan) > 0;
     CUdevResourceDesc dA, dB, dC;
-    if (devget(&dev, ctx->device) != CUDA_SUCCESS || getRes(dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return false;
-    if (split(grp, &n, &all, &rest, 0, (unsigned)want) != CUDA_SUCCESS || n < 1 || rest.sm.smCount == 0) return false;
-    bool three = false;
-    if (want_scan > 0 && (unsigned)want_scan + 8 <= rest.sm.smCount) {
-        n = 1;
-        three = split(sgrp, &n, &rest, &rest2, 0, (unsigned)want_scan) == CUDA_SUCCESS && n >= 1 && rest2.sm.smCount > 0;
-    }
-    CUdevResource &bulk = three ? rest2 : rest;
     CUgreenCtx gl = nullptr, gb = nullptr, gs = nullptr;
-    bool ok = genDesc(&dA, &grp[0], 1) == CUDA_SUCCESS && genDesc(&dB, &bulk, 1) == CUDA_SUCCESS &&
-              (!three || genDesc(&dC, &sgrp[0], 1) == CUDA_SUCCESS);
-    ok = ok && gcreate(&gl, dA, dev, CU_GREEN_CTX_DEFAULT_STREAM) == CUDA_SUCCESS;
-    ok = ok && gcreate(&gb, dB, dev, CU_GREEN_CTX_DEFAULT_STREAM) == CUDA_SUCCESS;
-    ok = ok && (!three || gcreate(&gs, dC, dev, CU_GREEN_CTX_DEFAULT_STREAM) == CUDA_SUCCESS);
+    bool ok = G.genDesc(&dA, res_long.data(), (unsigned)res_long.size()) == CUDA_SUCCESS &&
+              G.genDesc(&dB, res_bulk.data(), (unsigned)res_bulk.size()) == CUDA_SUCCESS &&
+              (!three || G.genDesc(&dC, res_scan.data(), (unsigned)res_scan.size()) == CUDA_SUCCESS);
+    ok = ok && G.gcreate(&gl, dA, dev, CU_GREEN_CTX_DEFAULT_STREAM) == CUDA_SUCCESS;
+    ok = ok && G.gcreate(&gb, dB, dev, CU_GREEN_CTX_DEFAULT_STREAM) == CUDA_SUCCESS;
+    ok = ok && (!three || G.gcreate(&gs, dC, dev, CU_GREEN_CTX_DEFAULT_STREAM) == CUDA_SUCCESS);
     cudaStream_t a[N_STREAMS] = {}, b[N_STREAMS] = {}, c[N_SCAN_STREAMS] = {};
     for (int i = 0; i < ctx->n_slots && ok; i++) {
         CUstream sa = nullptr, sb = nullptr;
-        ok = gstream(&sb, gb, CU_STREAM_NON_BLOCKING, 0) == CUDA_SUCCESS;
+        ok = G.gstream(&sb, gb, CU_STREAM_NON_BLOCKING, 0) == CUDA_SUCCESS;
         if (ok) b[i] = (cudaStream_t)sb;
-        ok = ok && gstream(&sa, gl, CU_STREAM_NON_BLOCKING, 0) == CUDA_SUCCESS;
+        ok = ok && G.gstream(&sa, gl, CU_STREAM_NON_BLOCKING, 0) == CUDA_SUCCESS;
         if (ok) a[i] = (cudaStream_t)sa;
     }
     for (int i = 0; i < N_SCAN_STREAMS && ok && three; i++) {
         CUstream sc = nullptr;
-        ok = gstream(&sc, gs, CU_STREAM_NON_BLOCKING, 0) == CUDA_SUCCESS;
+        ok = G.gstream(&sc, gs, CU_STREAM_NON_BLOCKING, 0) == CUDA_SUCCESS;
         if (ok) c[i] = (cudaStream_t)sc;
     }
-    if (!ok) {   // half-made: nothing of it reaches the context
+    if (!ok) {
         for (int i = 0; i < N_STREAMS; i++) { if (a[i]) cudaStreamDestroy(a[i]); if (b[i]) cudaStreamDestroy(b[i]); }
         for (int i = 0; i < N_SCAN_STREAMS; i++) if (c[i]) cudaStreamDestroy(c[i]);
-        if (gdestroy) { if (gl) gdestroy(gl); if (gb) gdestroy(gb); if (gs) gdestroy(gs); }
+        if (G.gdestroy) { if (gl) G.gdestroy(gl); if (gb) G.gdestroy(gb); if (gs) G.gdestroy(gs); }
         (void)cudaGetLastError();
         return false;
     }
     for (int i = 0; i < N_STREAMS; i++) { ctx->streams[i] = b[i]; ctx->streams2[i] = a[i]; }
     for (int i = 0; i < N_SCAN_STREAMS; i++) ctx->scan_streams[i] = c[i];
     ctx->g_long = gl; ctx->g_bulk = gb; ctx->g_scan = gs;
-    ctx->part_sms = (int)grp[0].sm.smCount;
-    ctx->bulk_sms = (int)bulk.sm.smCount;
-    ctx->scan_sms = three ? (int)sgrp[0].sm.smCount : 0;
+    ctx->part_sms = (int)count(res_long);
+    ctx->bulk_sms = (int)count(res_bulk);
+    ctx->scan_sms = three ? (int)count(res_scan) : 0;
     ctx->sm_count = ctx->bulk_sms;   // persistent kernels on the bulk streams (CRC-32, ...) size their grid to the bulk partition
     return true;
+}
+
+// Spatial partition with CUDA green contexts (driver API resolved at run time so the library does not link libcuda):
+// `want` SMs for the long-chunk latency kernels, `want_scan` SMs for the front halves (K1 is a whole-SM persistent
+// kernel that cannot be placed on an SM holding SHA blocks), the rest for everything else.  ONE split call cuts the
+// device into groups of `unit` SMs (outputs of one split may be combined into one descriptor); if the driver refuses,
+// the two-way split of round 1 (long / rest) is tried, and without green contexts the context runs unpartitioned.
+static bool make_partition(pbsgpu_ctx *ctx, int want, int want_scan) {
+    const GreenApi G = green_api();
+    if (!G.ok()) return false;
+    cudaFree(0);   // make sure the primary context exists
+    CUdevice dev;
+    CUdevResource all;
+    if (G.devget(&dev, ctx->device) != CUDA_SUCCESS || G.getRes(dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return false;
+    const unsigned unit = 8;
+    if (want_scan > 0) {
+        CUdevResource grp[64], rem;
+        unsigned n = 64;
+        const CUresult sr = G.split(grp, &n, &all, &rem, 0, unit);
+        if (getenv("PBSGPU_DEBUG")) fprintf(stderr, "[pbsgpu] split(all=%u SMs, unit %u) -> rc %d, %u groups of %u, remainder %u\n",
+                                            all.sm.smCount, unit, (int)sr, n, n ? grp[0].sm.smCount : 0, rem.sm.smCount);
+        if (sr == CUDA_SUCCESS && n >= 3) {
+            const unsigned gsz = grp[0].sm.smCount ? grp[0].sm.smCount : unit;
+            const unsigned kl = std::max(1u, ((unsigned)want + gsz - 1) / gsz), ks = std::max(1u, ((unsigned)want_scan + gsz - 1) / gsz);
+            if (kl + ks < n) {
+                std::vector<CUdevResource> L(grp, grp + kl), S(grp + kl, grp + kl + ks), B(grp + kl + ks, grp + n);
+                if (rem.sm.smCount > 0) B.push_back(rem);
+                if (adopt_partition(ctx, G, dev, L, S, B)) return true;
+                if (getenv("PBSGPU_DEBUG")) fprintf(stderr, "[pbsgpu] 3-way partition (%u + %u groups) refused, trying 2-way\n", kl, ks);
+            }
+        }
+        (void)cudaGetLastError();
+    }
+    CUdevResource grp[1], rest;
+    unsigned n = 1;
+    if (G.split(grp, &n, &all, &rest, 0, (unsigned)want) != CUDA_SUCCESS || n < 1 || rest.sm.smCount == 0) return false;
+    return adopt_partition(ctx, G, dev, {grp[0]}, {}, {rest});
 }
 
 static void ctx_destroy(pbsgpu_ctx *ctx) {

@@ -13,7 +13,7 @@ if m:
 else: print(sys.argv[1], 'FAILED', t[-300:])
 PY
 }
-run scan24 X=1 | tee -a gpurun_out/r2f_sweep.txt
+run scan24 PBSGPU_DEBUG=1 | tee -a gpurun_out/r2f_sweep.txt
 run scan0 PBSGPU_SCAN_SMS=0 | tee -a gpurun_out/r2f_sweep.txt
 run scan16 PBSGPU_SCAN_SMS=16 | tee -a gpurun_out/r2f_sweep.txt
 run scan32 PBSGPU_SCAN_SMS=32 | tee -a gpurun_out/r2f_sweep.txt
