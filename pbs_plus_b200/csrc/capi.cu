@@ -274,8 +274,9 @@ extern "C" int pbsgpu_open(int device, pbsgpu_ctx **out) {
         const int side_prio = env_int("PBSGPU_HYBRID_PRIO", 0) ? prio_hi : prio_lo;   // 1: long-chunk kernels on a high-priority stream
         // default: 24 SMs reserved for the long-chunk latency kernels (green contexts); 0 disables
         const int want_part = env_int("PBSGPU_PARTITION_SMS", 24);
-        // + PBSGPU_SCAN_SMS (default 24) SMs that run only the front halves (K1 scan / sort / K2); 0 = scans share the bulk partition
-        const int want_scan = env_int("PBSGPU_SCAN_SMS", 24);
+        // + PBSGPU_SCAN_SMS SMs that run only the front halves (K1 scan / sort / K2); default 0 = scans share the bulk partition
+        // (measured: a dedicated scan partition of 16-32 SMs LOWERS the pipelined throughput by 15-25 %, profiles/r02_partition3.txt)
+        const int want_scan = env_int("PBSGPU_SCAN_SMS", 0);
         const bool partitioned = want_part > 0 && want_part + 8 <= ctx->sm_count && make_partition(ctx, want_part, want_scan);
         bool ok = true;
         for (int i = 0; i < ctx->n_slots && !partitioned && ok; i++)

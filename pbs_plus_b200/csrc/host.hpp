@@ -69,9 +69,9 @@ struct pbsgpu_ctx {
     cudaEvent_t epoch = nullptr;   // recorded at open; kernel intervals are reported relative to it
     // optional spatial partition (CUDA green contexts): `part_sms` SMs are reserved for the latency
     // kernels of long chunks (streams2), everything else runs on the remaining SMs (streams)
-    // Round 2: a THIRD partition runs only the front halves (K1 is a whole-SM persistent kernel -- 207 KB of shared memory,
-    // 49 k registers per CTA -- that cannot be placed on an SM holding SHA blocks; sharing SMs with K3 it starved for
-    // up to 1.2 s behind resident SHA blocks, profiles/r02_partition3.txt)
+    // Round 2: an optional THIRD partition (PBSGPU_SCAN_SMS, default off) runs only the front halves: K1 is a whole-SM
+    // persistent kernel (207 KB of shared memory, 49 k registers per CTA) that cannot be placed on an SM holding SHA
+    // blocks.  Measured 15-25 % SLOWER than sharing the bulk partition (profiles/r02_partition3.txt).
     int part_sms = 0, bulk_sms = 0, scan_sms = 0;
     CUgreenCtx g_long = nullptr, g_bulk = nullptr, g_scan = nullptr;
     // knobs, read from the environment ONCE PER CONTEXT in pbsgpu_open (never process-wide statics)
