@@ -8,7 +8,7 @@ import subprocess
 import sys
 
 ALU = {"SHF", "LOP3", "IADD3", "PRMT", "SEL", "ISETP", "VIADD", "IADD", "LEA", "MOV", "VABSDIFF", "IMNMX", "FSEL", "PLOP3", "SGXT", "BMSK", "FLO", "POPC"}
-MIN_LOOP = 300   # instructions; smaller loops are not the block loop
+MIN_LOOP = 200   # instructions; smaller loops are not the block loop
 FMA = {"IMAD", "FFMA", "FMUL", "FADD", "HFMA2"}
 
 
