@@ -270,7 +270,9 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 1) k_scan_tuned(ScanArgs a
             uint32_t q = 0, acc = 1;
             const uint4 *data = (const uint4 *)(buf + lane * LANE_SPAN);
             lane_block<false, 4>(data, rotb, laneoff, Q, M, q, acc);   // halo: warm-up, no test
-#pragma unroll 1
+            // fully unrolled: in a rolled loop every byte costs an extra register move (the ring slot Q[p] must return to
+            // its canonical register at the back-edge); unrolled, the renaming is free (65 -> ~10 IMAD.MOV per 64 B)
+#pragma unroll
             for (int it = 1; it <= 4; it++) lane_block<true, 4>(data + it * 4, rotb, laneoff, Q, M, q, acc);
             lane_block<true, 1>(data + 20, rotb, laneoff, Q, M, q, acc);  // 272 = 4*64 + 16
             if (!acc) lane_exact(a, buf, rot, lane, cur);
@@ -307,13 +309,6 @@ uint64_t scan_lanes_super_bytes() { return LS_SUPER; }
 uint32_t scan_lanes_align() { return LS_ALIGN; }
 uint32_t scan_lanes_steps() { return LS_STEPS; }
 
-struct StepInfo {
-    uint32_t stream;
-    uint32_t kind;        // 0 = plain tile, 1 = step of a super-tile
-    uint32_t valid;       // plain tile: bytes of the stream in the tile
-    uint32_t k;           // super-tile: step 0..LS_STEPS-1
-    uint64_t stream_pos;  // stream offset of the tile / super-tile
-};
 
 // Exact walk of one lane's 256 B piece (slow path of k_scan_lanes).  The piece is in shared memory; the 64 bytes
 // before it left shared memory a step ago, so they come back from global memory (L2) as four 16 B loads.
@@ -342,6 +337,39 @@ __device__ __noinline__ void piece_exact(const ScanArgs &a, const uint8_t *row, 
         if (pos >= 63 && (h & a.mask) >= a.break_min) emit_candidate(a, stream, pos);
     }
 }
+
+// 64 bytes whose four 16 B vectors the caller has loaded (lane-contiguous kernel: swizzled shared addresses)
+template <bool TEST>
+__device__ __forceinline__ void lane_block_v(const uint4 (&dv)[4], const uint8_t *rotb, uint32_t laneoff, uint32_t (&Q)[64],
+                                             const uint32_t (&M)[32], uint32_t &q, uint32_t &acc) {
+#pragma unroll
+    for (int v = 0; v < 4; v++) {
+        const uint32_t w[4] = {dv[v].x, dv[v].y, dv[v].z, dv[v].w};
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            const int p = v * 16 + j;
+            uint32_t idx = __byte_perm(w[j >> 2], laneoff, 0x5504 | ((j & 3) << 4));  // b<<8 | lane*4
+            uint32_t val = *(const uint32_t *)(rotb + idx + (p & 31) * 4);
+            q ^= val;
+            if (TEST) test_acc(q, Q[p], M[p & 31], acc);
+            Q[p] = q;
+        }
+    }
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+
+// Work unit of k_scan_lanes: a super-tile (8 steps) or a plain tile.
+struct LsUnit {
+    uint32_t stream;
+    uint32_t kind;        // 0 = plain tile, 1 = super-tile
+    uint32_t valid;       // plain tile: bytes of the stream in the tile
+    uint64_t stream_pos;  // stream offset of the tile / super-tile
+    uint64_t soff;        // a.off[stream]
+};
 
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 1) k_scan_lanes(ScanArgs a, const uint32_t *__restrict__ rot_g,
                                                                        const __grid_constant__ CUtensorMap tmap) {
@@ -382,36 +410,42 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 1) k_scan_lanes(ScanArgs a
 #pragma unroll
     for (int k = 0; k < 32; k++) M[k] = rotr32(m21, (k + lane) & 31);
     const uint32_t laneoff = lane * 4;
+    // SWIZZLE_128B: 16 B chunk cc of the lane's 128 B row sits at (cc ^ (lane & 7)) << 4 -- eight per-lane constants
+    uint32_t swz[8];
+#pragma unroll
+    for (int cc = 0; cc < 8; cc++) swz[cc] = ((uint32_t)cc ^ (lane & 7)) << 4;
 
-    // step cursor: tile_first[] counts STEPS (a super-tile is LS_STEPS of them, a plain tile one)
+    // unit cursor: tile_first[] counts STEPS (a super-tile is LS_STEPS of them, a plain tile one); all the bookkeeping
+    // below runs once per UNIT (64 KiB), not once per step
     uint32_t s = find_stream(a.tile_first, a.n_streams, u0);
     uint64_t s_first = a.tile_first[s], s_next = a.tile_first[s + 1];
-    uint64_t s_ns = n_super_of(s);
+    uint64_t s_ns = n_super_of(s), s_off = a.off[s], s_len = a.len[s];
     uint64_t u = u0;
-    auto next_step = [&](StepInfo &st) -> bool {
+    auto next_unit = [&](LsUnit &un) -> bool {
         if (u >= u1) return false;
-        while (u >= s_next) { s++; s_first = s_next; s_next = a.tile_first[s + 1]; s_ns = n_super_of(s); }
+        while (u >= s_next) { s++; s_first = s_next; s_next = a.tile_first[s + 1]; s_ns = n_super_of(s); s_off = a.off[s]; s_len = a.len[s]; }
         const uint64_t j = u - s_first;
-        st.stream = s;
+        un.stream = s; un.soff = s_off;
         if (j < s_ns * LS_STEPS) {
-            st.kind = 1; st.k = (uint32_t)(j % LS_STEPS); st.valid = 0; st.stream_pos = (j / LS_STEPS) * LS_SUPER;
+            un.kind = 1; un.valid = 0; un.stream_pos = (j / LS_STEPS) * LS_SUPER;
+            u += LS_STEPS;
         } else {
-            st.kind = 0; st.k = 0;
-            st.stream_pos = s_ns * LS_SUPER + (j - s_ns * LS_STEPS) * WARP_TILE;
-            const uint64_t rem = a.len[s] - st.stream_pos;
-            st.valid = rem < (uint64_t)WARP_TILE ? (uint32_t)rem : (uint32_t)WARP_TILE;
+            un.kind = 0;
+            un.stream_pos = s_ns * LS_SUPER + (j - s_ns * LS_STEPS) * WARP_TILE;
+            const uint64_t rem = s_len - un.stream_pos;
+            un.valid = rem < (uint64_t)WARP_TILE ? (uint32_t)rem : (uint32_t)WARP_TILE;
+            u += 1;
         }
-        u++;
         return true;
     };
-    auto issue = [&](const StepInfo &st, int b) {
+    // step k of super-tile `un` into buffer b: ONE tensor-map copy brings the 256 B piece of every lane -- box {128 B, 1,
+    // 32 lanes (stride 2 KiB), 2 halves}, SWIZZLE_128B -> shared [half][lane][128 B] (SASS UTMALDG); only step 0 adds the
+    // per-lane 64 B halos.  The caller has made sure (syncwarp) that every lane is done with buffer b.
+    auto issue_super = [&](const LsUnit &un, uint32_t k, int b) {
         uint8_t *buf = buf0 + b * LS_BUF;
-        const uint8_t *sbase = a.base + a.off[st.stream];
-        if (st.kind == 1) {
-            // ONE tensor-map copy brings the 256 B piece of every lane: box {128 B, 1, 32 lanes (stride 2 KiB), 2 halves},
-            // SWIZZLE_128B -> shared [half][lane][128 B] (SASS UTMALDG); only step 0 adds the per-lane 64 B halos.
-            const uint64_t lane_start = st.stream_pos + (uint64_t)lane * LS_R;
-            const bool first_of_stream = st.k == 0 && lane_start == 0;      // only lane 0 of the stream's first super-tile
+        if (k == 0) {
+            const uint64_t lane_start = un.stream_pos + (uint64_t)lane * LS_R;
+            const bool first_of_stream = lane_start == 0;                  // only lane 0 of the stream's first super-tile
             uint8_t *halo = buf + LS_BOX + lane * LS_HALO_STRIDE;
             if (first_of_stream) {
                 uint32_t *hz = (uint32_t *)halo;
@@ -419,65 +453,95 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 1) k_scan_lanes(ScanArgs a
                 for (int i = 0; i < 16; i++) hz[i] = 0;                     // zero halo (positions < 63 are never reported)
             }
             const uint32_t any_first = __ballot_sync(0xffffffffu, first_of_stream);
-            const uint32_t bytes = LS_BOX + (st.k == 0 ? (32 - __popc(any_first)) * 64 : 0);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // this lane's earlier reads / writes of the buffer
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) {
-                mbar_arrive_expect_tx(bar_s[b], bytes);
-                const int c1 = (int)((a.off[st.stream] + st.stream_pos + (uint64_t)st.k * LS_PIECE) >> 7);   // 128 B unit of lane 0's piece
+                mbar_arrive_expect_tx(bar_s[b], LS_BOX + (32 - __popc(any_first)) * 64);
+                const int c1 = (int)((un.soff + un.stream_pos) >> 7);
                 asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
                              ::"r"(smem_u32(buf)), "l"(&tmap), "r"(0), "r"(c1), "r"(0), "r"(0), "r"(bar_s[b]) : "memory");
             }
             __syncwarp();
-            if (st.k == 0 && !first_of_stream) tma_bulk_g2s(smem_u32(halo), sbase + lane_start - 64, 64, bar_s[b]);
-        } else {
-            const uint8_t *src = sbase + st.stream_pos;
-            uint32_t halo = st.stream_pos ? HALO : 0;
-            uint32_t bytes = halo + st.valid;
-            const uint8_t *src0 = src - halo;
-            uint8_t *dst0 = buf + (HALO - halo);
-            if (!halo && lane < 16) ((uint32_t *)buf)[lane] = 0;
-            if ((((uintptr_t)src0) & 15) == 0) {
-                uint32_t bulk = bytes & ~15u;
-                for (uint32_t i = bulk + lane; i < bytes; i += 32) dst0[i] = src0[i];
-                __syncwarp();
-                if (lane == 0) {
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    mbar_arrive_expect_tx(bar_s[b], bulk);
-                    if (bulk) tma_bulk_g2s(smem_u32(dst0), src0, bulk, bar_s[b]);
-                }
-            } else {
-                for (uint32_t i = lane; i < bytes; i += 32) dst0[i] = src0[i];
-                __syncwarp();
-                if (lane == 0) mbar_arrive_expect_tx(bar_s[b], 0);
-            }
+            if (!first_of_stream) tma_bulk_g2s(smem_u32(halo), a.base + un.soff + lane_start - 64, 64, bar_s[b]);
+        } else if (lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive_expect_tx(bar_s[b], LS_BOX);
+            const int c1 = (int)((un.soff + un.stream_pos + (uint64_t)k * LS_PIECE) >> 7);   // 128 B unit of lane 0's piece
+            asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                         ::"r"(smem_u32(buf)), "l"(&tmap), "r"(0), "r"(c1), "r"(0), "r"(0), "r"(bar_s[b]) : "memory");
         }
     };
+    auto issue_plain = [&](const LsUnit &un, int b) {
+        uint8_t *buf = buf0 + b * LS_BUF;
+        const uint8_t *src = a.base + un.soff + un.stream_pos;
+        uint32_t halo = un.stream_pos ? HALO : 0;
+        uint32_t bytes = halo + un.valid;
+        const uint8_t *src0 = src - halo;
+        uint8_t *dst0 = buf + (HALO - halo);
+        if (!halo && lane < 16) ((uint32_t *)buf)[lane] = 0;
+        if ((((uintptr_t)src0) & 15) == 0) {
+            uint32_t bulk = bytes & ~15u;
+            for (uint32_t i = bulk + lane; i < bytes; i += 32) dst0[i] = src0[i];
+            __syncwarp();
+            if (lane == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive_expect_tx(bar_s[b], bulk);
+                if (bulk) tma_bulk_g2s(smem_u32(dst0), src0, bulk, bar_s[b]);
+            }
+        } else {
+            for (uint32_t i = lane; i < bytes; i += 32) dst0[i] = src0[i];
+            __syncwarp();
+            if (lane == 0) mbar_arrive_expect_tx(bar_s[b], 0);
+        }
+    };
+    auto issue_first = [&](const LsUnit &un, int b) { if (un.kind == 1) issue_super(un, 0, b); else issue_plain(un, b); };
 
     uint32_t Q[64];
     uint32_t q = 0;
-    StepInfo cur, nxt;
-    bool have = next_step(cur);
-    if (have) issue(cur, 0);
-    for (uint64_t n = 0; have; n++) {
-        const int b = (int)(n & 1);
-        const bool have_next = next_step(nxt);
-        if (have_next) issue(nxt, b ^ 1);
-        mbar_wait(bar_s[b], (uint32_t)((n >> 1) & 1));
-        const uint8_t *buf = buf0 + b * LS_BUF;
-        uint32_t acc = 1;
+    LsUnit cur, nxt;
+    bool have = next_unit(cur);
+    if (have) issue_first(cur, 0);
+    uint32_t n = 0;   // steps processed by this warp: buffer = n & 1, mbarrier parity = (n >> 1) & 1
+    while (have) {
+        const bool have_next = next_unit(nxt);
         if (cur.kind == 1) {
-            const uint4 *row = (const uint4 *)(buf + lane * 128);      // the lane's row of half 0 in the swizzled tile
-            if (cur.k == 0) {
-                q = 0;
-                lane_block<false, 4>((const uint4 *)(buf + LS_BOX + lane * LS_HALO_STRIDE), rotb, laneoff, Q, M, q, acc);
-            }
 #pragma unroll 1
-            for (int it = 0; it < 4; it++) lane_block<true, 4, true>(row, rotb, laneoff, Q, M, q, acc, (uint32_t)it * 4, lane & 7);
-            if (!acc)
-                piece_exact(a, (const uint8_t *)row, rot, lane, cur.stream, a.base + a.off[cur.stream],
-                            cur.stream_pos + (uint64_t)lane * LS_R + (uint64_t)cur.k * LS_PIECE);
+            for (uint32_t k = 0; k < LS_STEPS; k++, n++) {
+                const int b = (int)(n & 1);
+                if (k + 1 < LS_STEPS) issue_super(cur, k + 1, b ^ 1);
+                else if (have_next) issue_first(nxt, b ^ 1);
+                mbar_wait(bar_s[b], (n >> 1) & 1);
+                const uint8_t *buf = buf0 + b * LS_BUF;
+                uint32_t acc = 1;
+                if (k == 0) {
+                    q = 0;
+                    lane_block<false, 4>((const uint4 *)(buf + LS_BOX + lane * LS_HALO_STRIDE), rotb, laneoff, Q, M, q, acc);
+                }
+                const uint32_t row = smem_u32(buf) + lane * 128;          // the lane's row of half 0 in the swizzled tile
+                uint32_t ad[8];
+#pragma unroll
+                for (int cc = 0; cc < 8; cc++) ad[cc] = row + swz[cc];
+#pragma unroll
+                for (int it = 0; it < 4; it++) {                            // 4 x 64 B, all addresses compile-time + ad[]
+                    uint4 dv[4];
+#pragma unroll
+                    for (int v = 0; v < 4; v++) {
+                        const int V = it * 4 + v;
+                        dv[v] = lds128(ad[V & 7] + ((V >> 3) << 12));
+                    }
+                    lane_block_v<true>(dv, rotb, laneoff, Q, M, q, acc);
+                }
+                if (!acc)
+                    piece_exact(a, buf + lane * 128, rot, lane, cur.stream, a.base + cur.soff,
+                                cur.stream_pos + (uint64_t)lane * LS_R + (uint64_t)k * LS_PIECE);
+                __syncwarp();
+            }
         } else {
+            const int b = (int)(n & 1);
+            if (have_next) issue_first(nxt, b ^ 1);
+            mbar_wait(bar_s[b], (n >> 1) & 1);
+            const uint8_t *buf = buf0 + b * LS_BUF;
+            uint32_t acc = 1;
             TileInfo ti;
             ti.stream = cur.stream; ti.valid = cur.valid; ti.stream_pos = cur.stream_pos;
             if (cur.valid == WARP_TILE) {
@@ -491,8 +555,9 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 1) k_scan_lanes(ScanArgs a
             } else {
                 lane_exact(a, buf, rot, lane, ti);
             }
+            __syncwarp();
+            n++;
         }
-        __syncwarp();
         cur = nxt;
         have = have_next;
     }
