@@ -491,6 +491,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                                                         "sha_bulk_ms", "set_ms", "total_ms")},
         },
     }
+    if args.timeline:
+        out["timeline"] = [{k: round(float(t[k]), 2) for k in ("scan_t0", "scan_t1", "sha_t0", "sha_t1", "sha_long_ms", "sha_bulk_ms", "total_ms")}
+                           for t in timings]
     # ---- untimed post-run parity check: the record list of the LAST timed step equals the oracle's
     last_rec = results[-1][0]
     if world == 1 and not args.no_verify and not reduced and args.avg_kib == 4096:
@@ -774,6 +777,7 @@ def main():
     ap.add_argument("--avg-kib", type=int, default=4096, help="diagnostic only; the metric is quoted at 4096")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4verify"])
     ap.add_argument("--emulate-ranks", default="2,4,8", help="cfg4verify: world sizes to produce expected hit counts for")
+    ap.add_argument("--timeline", action="store_true", help="add per-step kernel intervals (ms since context open) to the line")
     ap.add_argument("--no-verify", action="store_true", help="skip the untimed post-run comparison with the oracle")
     ap.add_argument("--no-distinct", action="store_true", help="skip the non-repeating-data figure (value_distinct)")
     ap.add_argument("--distinct-gib", type=int, default=768)

@@ -1,15 +1,16 @@
 #!/bin/bash
-# Round 2, call E: compute-sanitizer over the round-2 kernels, lone-chain speed of the new consumer (CMODE 2), ncu launch list of
-# one bench step + full captures of K1/K3 in the real batch (traffic for the r02 roofline line).
+# Round 2, call E: timeline of the pipelined run, compute-sanitizer over the round-2 kernels, ncu launch list of one bench step +
+# full captures of K1/K3 in the real batch (traffic for the r02 roofline line).
 mkdir -p gpurun_out
 export CUDA_DEVICE_MAX_CONNECTIONS=32
+timeout 300 python bench.py --steps 20 --warmup 3 --no-e2e --no-cpu --no-verify --no-distinct --timeline > gpurun_out/r2e_timeline.txt 2>&1; tail -c 300 gpurun_out/r2e_timeline.txt
+timeout 300 python bench.py --steps 20 --warmup 3 --no-e2e --no-cpu --no-verify --no-distinct --timeline > gpurun_out/r2e_timeline2.txt 2>&1; tail -c 200 gpurun_out/r2e_timeline2.txt
 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_round2.py -q -x \
     -k "suggested or payload or async_jobs or dense_batch or blob or reserve_commit or single_rank" > gpurun_out/r2e_san_memcheck.txt 2>&1; echo "memcheck rc=$?" | tee -a gpurun_out/r2e_san_memcheck.txt
 PBSGPU_SCAN_LANES=1 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -q -x \
     -k "scan_lanes" > gpurun_out/r2e_san_lanes.txt 2>&1; echo "memcheck lanes rc=$?" | tee -a gpurun_out/r2e_san_lanes.txt
-timeout 600 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_round2.py -q -x \
-    -k "async_jobs or dense_batch" > gpurun_out/r2e_san_racecheck.txt 2>&1; echo "racecheck rc=$?" | tee -a gpurun_out/r2e_san_racecheck.txt
-timeout 300 ./tools/sha_lab.bin load 1024 4 > gpurun_out/r2e_sha_lab_load_split.txt 2>&1; grep -E "m=0.25|m=1.00|m=4.00" gpurun_out/r2e_sha_lab_load_split.txt
+timeout 600 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_round2.py tests/test_gpu_parity.py -q -x \
+    -k "async_jobs or dense_batch or scan_ragged" > gpurun_out/r2e_san_racecheck.txt 2>&1; echo "racecheck rc=$?" | tee -a gpurun_out/r2e_san_racecheck.txt
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2e_launches.csv \
     python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu --no-verify --no-distinct > gpurun_out/r2e_launches_bench.log 2>&1; tail -c 300 gpurun_out/r2e_launches_bench.log
 for k in k_scan_tuned k_sha_tuned k_sha_split; do
