@@ -706,7 +706,7 @@ def ncu_traffic():
     """dram bytes (read + write) per launch of EVERY kernel class of the step, from the committed ncu --set full
     summaries of one 64 GiB batch: K1 scan reads the input once, K3 (bulk + long-chunk kernel) reads it again."""
     import re
-    files = {"K1_scan": ("r01_ncu_k_scan_tuned.txt",), "K3_sha_bulk": ("r01_ncu_k_sha_tuned.txt",), "K3_sha_long": ("r01_ncu_k_sha_split.txt",)}
+    files = {"K1_scan": ("r02_ncu_batch_k_scan_tuned.txt",), "K3_sha_bulk": ("r02_ncu_batch_k_sha_tuned.txt",), "K3_sha_long": ("r02_ncu_batch_k_sha_split.txt",)}
     out, tot = {}, 0.0
     for key, names in files.items():
         for name in names:
@@ -725,7 +725,7 @@ def ncu_traffic():
             tot += b
     alg = 1024 * (64 << 20)
     out.update({"total": tot, "algorithmic": alg, "ratio_to_algorithmic": tot / alg,
-                "source": "profiles/r01_ncu_k_scan_tuned.txt + r01_ncu_k_sha_tuned.txt + r01_ncu_k_sha_split.txt (one 64 GiB batch each); "
+                "source": "profiles/r02_ncu_batch_k_scan_tuned.txt + r02_ncu_batch_k_sha_tuned.txt + r02_ncu_batch_k_sha_split.txt (ncu --set full of one launch each inside `bench.py --steps 2`, one 64 GiB batch); "
                           "the input is read twice (K1, then K3): 2.0 x the algorithmic bytes; K7 (xxh3) is not part of the step"})
     return out
 
