@@ -140,11 +140,12 @@ static bool adopt_partition(pbsgpu_ctx *ctx, const GreenApi &G, CUdevice dev, st
     ok = ok && G.gcreate(&gl, dA, dev, CU_GREEN_CTX_DEFAULT_STREAM) == CUDA_SUCCESS;
     ok = ok && G.gcreate(&gb, dB, dev, CU_GREEN_CTX_DEFAULT_STREAM) == CUDA_SUCCESS;
     ok = ok && (!three || G.gcreate(&gs, dC, dev, CU_GREEN_CTX_DEFAULT_STREAM) == CUDA_SUCCESS);
-    cudaStream_t a[N_STREAMS] = {}, b[N_STREAMS] = {}, c[N_SCAN_STREAMS] = {};
+    cudaStream_t a[N_STREAMS] = {}, b[N_STREAMS] = {}, c[N_SCAN_STREAMS] = {}, m[N_STREAMS] = {};
     for (int i = 0; i < ctx->n_slots && ok; i++) {
-        CUstream sa = nullptr, sb = nullptr;
+        CUstream sa = nullptr, sb = nullptr, sm = nullptr;
         ok = G.gstream(&sb, gb, CU_STREAM_NON_BLOCKING, 0) == CUDA_SUCCESS;
         if (ok) b[i] = (cudaStream_t)sb;
+        if (ok && ctx->tune.mid_x10 > 0) { ok = G.gstream(&sm, gb, CU_STREAM_NON_BLOCKING, -1) == CUDA_SUCCESS; if (ok) m[i] = (cudaStream_t)sm; }
         ok = ok && G.gstream(&sa, gl, CU_STREAM_NON_BLOCKING, 0) == CUDA_SUCCESS;
         if (ok) a[i] = (cudaStream_t)sa;
     }
@@ -154,13 +155,13 @@ static bool adopt_partition(pbsgpu_ctx *ctx, const GreenApi &G, CUdevice dev, st
         if (ok) c[i] = (cudaStream_t)sc;
     }
     if (!ok) {
-        for (int i = 0; i < N_STREAMS; i++) { if (a[i]) cudaStreamDestroy(a[i]); if (b[i]) cudaStreamDestroy(b[i]); }
+        for (int i = 0; i < N_STREAMS; i++) { if (a[i]) cudaStreamDestroy(a[i]); if (b[i]) cudaStreamDestroy(b[i]); if (m[i]) cudaStreamDestroy(m[i]); }
         for (int i = 0; i < N_SCAN_STREAMS; i++) if (c[i]) cudaStreamDestroy(c[i]);
         if (G.gdestroy) { if (gl) G.gdestroy(gl); if (gb) G.gdestroy(gb); if (gs) G.gdestroy(gs); }
         (void)cudaGetLastError();
         return false;
     }
-    for (int i = 0; i < N_STREAMS; i++) { ctx->streams[i] = b[i]; ctx->streams2[i] = a[i]; }
+    for (int i = 0; i < N_STREAMS; i++) { ctx->streams[i] = b[i]; ctx->streams2[i] = a[i]; ctx->streams3[i] = m[i]; }
     for (int i = 0; i < N_SCAN_STREAMS; i++) ctx->scan_streams[i] = c[i];
     ctx->g_long = gl; ctx->g_bulk = gb; ctx->g_scan = gs;
     ctx->part_sms = (int)count(res_long);
@@ -214,6 +215,7 @@ static void ctx_destroy(pbsgpu_ctx *ctx) {
     for (int i = 0; i < N_STREAMS; i++) {
         if (ctx->streams[i]) cudaStreamDestroy(ctx->streams[i]);
         if (ctx->streams2[i]) cudaStreamDestroy(ctx->streams2[i]);
+        if (ctx->streams3[i]) cudaStreamDestroy(ctx->streams3[i]);
     }
     for (int i = 0; i < N_SCAN_STREAMS; i++) if (ctx->scan_streams[i]) cudaStreamDestroy(ctx->scan_streams[i]);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -265,6 +267,7 @@ extern "C" int pbsgpu_open(int device, pbsgpu_ctx **out) {
         ctx->tune.serial = env_int("PBSGPU_HYBRID_SERIAL", ctx->tune.serial);
         ctx->tune.spread_kb = env_int("PBSGPU_SPLIT_SPREAD_KB", ctx->tune.spread_kb);
         ctx->tune.head_per_sm = std::max(1, env_int("PBSGPU_HYBRID_HEAD_PER_SM", ctx->tune.head_per_sm));
+        ctx->tune.mid_x10 = std::max(0, env_int("PBSGPU_BULK_MID_X10", ctx->tune.mid_x10));
         ctx->n_slots = std::max(1, std::min(N_STREAMS, env_int("PBSGPU_SLOTS", ctx->n_slots)));
         ctx->crc_variant = env_int("PBSGPU_CRC_VARIANT", 0);
         if (getenv("PBSGPU_STREAM_WINDOW")) ctx->stream_window = strtoull(getenv("PBSGPU_STREAM_WINDOW"), nullptr, 0);
@@ -281,7 +284,8 @@ extern "C" int pbsgpu_open(int device, pbsgpu_ctx **out) {
         bool ok = true;
         for (int i = 0; i < ctx->n_slots && !partitioned && ok; i++)
             ok = cudaStreamCreateWithFlags(&ctx->streams[i], cudaStreamNonBlocking) == cudaSuccess &&
-                 cudaStreamCreateWithPriority(&ctx->streams2[i], cudaStreamNonBlocking, side_prio) == cudaSuccess;
+                 cudaStreamCreateWithPriority(&ctx->streams2[i], cudaStreamNonBlocking, side_prio) == cudaSuccess &&
+                 (ctx->tune.mid_x10 <= 0 || cudaStreamCreateWithPriority(&ctx->streams3[i], cudaStreamNonBlocking, prio_hi) == cudaSuccess);
         if (!ok || cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
             cudaStreamCreateWithFlags(&ctx->tail_stream, cudaStreamNonBlocking) != cudaSuccess) { rc = PBSGPU_ECUDA; break; }
         ctx->streams_made = true;
@@ -360,6 +364,7 @@ cudaError_t pbsgpu_job_sync(pbsgpu_job *j) {   // everything the job enqueued, o
     if (j->ss && j->ss != j->st && (r = cudaStreamSynchronize(j->ss)) != cudaSuccess) e = r;
     if (j->st && (r = cudaStreamSynchronize(j->st)) != cudaSuccess) e = r;
     if (j->st2 && (r = cudaStreamSynchronize(j->st2)) != cudaSuccess) e = r;
+    if (j->st3 && (r = cudaStreamSynchronize(j->st3)) != cudaSuccess) e = r;
     if (j->enqueued && j->have_events && (r = cudaEventSynchronize(j->ev[EV_END])) != cudaSuccess) e = r;
     if (e != cudaSuccess) (void)cudaGetLastError();
     return e;
@@ -415,7 +420,7 @@ static int job_alloc(pbsgpu_job *j) {
     DALLOC(j->d_cand, uint64_t, j->cand_cap);
     DALLOC(j->d_cand_sorted, uint64_t, j->cand_cap);
     if (!j->forced_keys.empty()) DALLOC(j->d_forced, uint64_t, j->forced_keys.size());
-    DALLOC(j->d_counters, unsigned long long, 4);
+    DALLOC(j->d_counters, unsigned long long, 8);
     DALLOC(j->d_counts, uint32_t, n + 1);
     DALLOC(j->d_chunk_first, uint64_t, n + 2);
     DALLOC(j->d_consumed, uint64_t, n + 1);
@@ -495,6 +500,7 @@ int pbsgpu_job_create(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg, const void *base_d
     if (j->cand_cap >= (1ull << 31)) { delete j; return fail(ctx, PBSGPU_EINVAL, "batch too large (candidate buffer)"); }
     j->st = ctx->streams[ctx->next_stream];
     j->st2 = ctx->streams2[ctx->next_stream];
+    j->st3 = ctx->streams3[ctx->next_stream];
     ctx->next_stream = (ctx->next_stream + 1) % ctx->n_slots;
     if (ctx->scan_sms > 0) { j->ss = ctx->scan_streams[ctx->next_scan]; ctx->next_scan = (ctx->next_scan + 1) % N_SCAN_STREAMS; }
     else j->ss = j->st;
@@ -532,7 +538,7 @@ int pbsgpu_job_enqueue_front(pbsgpu_job *j) {
     }
     CK(cudaMemcpyAsync(j->d_tile_first, j->tile_first.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
     if (j->d_forced) CK(cudaMemcpyAsync(j->d_forced, j->forced_keys.data(), j->forced_keys.size() * 8, cudaMemcpyHostToDevice, st));
-    CK(cudaMemsetAsync(j->d_counters, 0, 4 * sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(j->d_counters, 0, 8 * sizeof(unsigned long long), st));
     CK(cudaMemsetAsync(j->d_cand, 0xFF, j->cand_cap * 8, st));   // KEY_SENTINEL padding for the sort
     if (j->profiling) CK(cudaEventRecord(j->ev[EV_START], st));
     // K1
@@ -582,7 +588,7 @@ int pbsgpu_job_enqueue_back(pbsgpu_job *j) {
         ShaArgs ha;
         ha.base = j->base; ha.off = j->d_off; ha.chunks = j->d_chunks; ha.order = j->d_vals2;
         ha.n_chunks = &j->d_counters[1]; ha.chunk_cap = j->chunk_cap; ha.digests = j->d_digests;
-        ha.n_head = nullptr; ha.part = 0;
+        ha.n_head = nullptr; ha.n_mid = nullptr; ha.part = 0;
         if (j->variant == 1) CK(launch_sha_simple(ha, st));
         else if (!hybrid_for(ctx)) CK(launch_sha_tuned(ha, ctx->tune, st));
         else {
@@ -594,13 +600,26 @@ int pbsgpu_job_enqueue_back(pbsgpu_job *j) {
             uint32_t thr = thr64 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)thr64;
             // at most one latency CTA (32 chunks) per SM of the partition and job; the longest chunks first
             const unsigned long long max_head = (unsigned long long)ctx->tune.head_per_sm * (unsigned long long)(ctx->part_sms > 0 ? ctx->part_sms : 24);
-            CK(launch_split_point(j->d_keys2, &j->d_counters[1], j->chunk_cap, thr, max_head, &j->d_counters[2], st));
+            const bool use_mid = ctx->tune.mid_x10 > 0 && j->st3 != nullptr;
+            uint64_t thr_mid64 = (uint64_t)j->cfg.avg * (uint64_t)ctx->tune.mid_x10 / 10;
+            uint32_t thr_mid = thr_mid64 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)thr_mid64;
+            CK(launch_split_point(j->d_keys2, &j->d_counters[1], j->chunk_cap, thr, max_head, &j->d_counters[2], thr_mid,
+                                  use_mid ? &j->d_counters[4] : nullptr, st));
             CK(cudaEventRecord(j->ev[EV_FORK], st));
             if (!serial) CK(cudaStreamWaitEvent(side, j->ev[EV_FORK], 0));
             ha.n_head = &j->d_counters[2];
+            ha.n_mid = use_mid ? &j->d_counters[4] : nullptr;
             ha.part = 1; CK(launch_sha_split(ha, ctx->tune, side));
             CK(cudaEventRecord(j->ev[EV_JOIN], side));
-            ha.part = 2; CK(launch_sha_tuned(ha, ctx->tune, st));
+            if (use_mid) {   // the longer bulk chunks of every job in flight start first (high-priority stream), the short ones fill in
+                CK(cudaStreamWaitEvent(j->st3, j->ev[EV_FORK], 0));
+                ha.part = 3; CK(launch_sha_tuned(ha, ctx->tune, j->st3));
+                CK(cudaEventRecord(j->ev[EV_MID], j->st3));
+                ha.part = 4; CK(launch_sha_tuned(ha, ctx->tune, st));
+                CK(cudaStreamWaitEvent(st, j->ev[EV_MID], 0));
+            } else {
+                ha.part = 2; CK(launch_sha_tuned(ha, ctx->tune, st));
+            }
             CK(cudaEventRecord(j->ev[EV_BULK], st));
             if (!serial) CK(cudaStreamWaitEvent(st, j->ev[EV_JOIN], 0));
         }
@@ -969,7 +988,7 @@ extern "C" int pbsgpu_sha256_batch(pbsgpu_ctx *ctx, const void *base, const uint
     CK(cudaMemcpyAsync(d_n.p, &hn, 8, cudaMemcpyHostToDevice, st));
     ShaArgs ha;
     ha.base = dbase; ha.off = nullptr; ha.chunks = d_refs.as<ChunkRef>(); ha.order = nullptr; ha.n_chunks = d_n.as<unsigned long long>();
-    ha.chunk_cap = n; ha.digests = d_dig.as<uint8_t>(); ha.n_head = nullptr; ha.part = 0;
+    ha.chunk_cap = n; ha.digests = d_dig.as<uint8_t>(); ha.n_head = nullptr; ha.n_mid = nullptr; ha.part = 0;
     cudaError_t e = ctx->variant == 1 ? launch_sha_simple(ha, st) : launch_sha_tuned(ha, ctx->tune, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(digests, d_dig.p, (uint64_t)n * 32, cudaMemcpyDeviceToHost, st);
     cudaError_t es = cudaStreamSynchronize(st);   // always: the scoped blocks must not return to the pool while in use

@@ -49,6 +49,7 @@ struct pbsgpu_ctx {
     std::recursive_mutex mu;
     cudaStream_t streams[N_STREAMS] = {};
     cudaStream_t streams2[N_STREAMS] = {};   // forked side stream per job stream (latency kernel of the hybrid SHA launch)
+    cudaStream_t streams3[N_STREAMS] = {};   // PBSGPU_BULK_MID_X10 > 0: high-priority bulk stream per slot (mid class)
     cudaStream_t scan_streams[N_SCAN_STREAMS] = {};   // front halves (K1 scan, sort, K2 resolve) in submission order on the scan partition
     int next_scan = 0;
     cudaStream_t copy_stream = nullptr;
@@ -135,11 +136,11 @@ int pbsgpu_set_process_dev(pbsgpu_set *s, const uint8_t *d_dig, uint64_t n, int 
 // ---------------------------------------------------------------------------
 // Job: one batch of device-resident streams through K1..K4 on one CUDA stream (capi.cu)
 // ---------------------------------------------------------------------------
-enum { EV_START, EV_SCAN, EV_SORT, EV_RESOLVE, EV_SHA, EV_END, EV_FORK, EV_JOIN, EV_BULK, EV_BACK, EV_SET, EV_COUNT };
+enum { EV_START, EV_SCAN, EV_SORT, EV_RESOLVE, EV_SHA, EV_END, EV_FORK, EV_JOIN, EV_BULK, EV_BACK, EV_SET, EV_MID, EV_COUNT };
 
 struct pbsgpu_job {
     pbsgpu_ctx *ctx = nullptr;
-    cudaStream_t st = nullptr, st2 = nullptr, ss = nullptr;   // back half / long-chunk kernel / front half
+    cudaStream_t st = nullptr, st2 = nullptr, ss = nullptr, st3 = nullptr;   // back half / long-chunk kernel / front half / mid class
     pbsgpu_cfg cfg;
     const uint8_t *base = nullptr;
     std::vector<uint64_t> off, len, tile_first, forced_keys;   // forced_keys: (stream << 40 | offset-1) suggested boundaries
@@ -150,7 +151,7 @@ struct pbsgpu_job {
     pbsgpu_set *set = nullptr;      // fused probe + insert (NULL: none)
     // device
     uint64_t *d_off = nullptr, *d_len = nullptr, *d_tile_first = nullptr, *d_cand = nullptr, *d_cand_sorted = nullptr, *d_forced = nullptr;
-    unsigned long long *d_counters = nullptr;   // [0] cand_count [1] n_chunks [2] n_head [3] n_new (set)
+    unsigned long long *d_counters = nullptr;   // [0] cand_count [1] n_chunks [2] n_head [3] n_new (set) [4] n_mid
     uint32_t *d_counts = nullptr;
     uint64_t *d_chunk_first = nullptr, *d_consumed = nullptr;
     pbsgpu::ChunkRef *d_chunks = nullptr;

@@ -83,7 +83,9 @@ struct ShaArgs {
     // hybrid launch: the first *n_head entries of `order` (the longest chunks) go to the
     // latency-optimised split kernel (part 1), the rest to the throughput kernel (part 2).
     const unsigned long long *n_head;    // device; NULL with part 0
-    int part;                            // 0 = everything, 1 = head only, 2 = everything but the head
+    const unsigned long long *n_mid;     // device; end of the "mid" class (>= *n_head); NULL unless part is 3 or 4
+    int part;                            // 0 = everything, 1 = head only, 2 = everything but the head,
+                                         // 3 = mid class [head, mid), 4 = short class [mid, n)
 };
 // per-context tuning knobs of K3 (read from the environment once per pbsgpu_open)
 struct ShaTune {
@@ -93,13 +95,15 @@ struct ShaTune {
     int serial = 0;      // PBSGPU_HYBRID_SERIAL: latency kernel on the job's own stream (diagnostic)
     int spread_kb = 30;  // PBSGPU_SPLIT_SPREAD_KB: dummy dynamic shared memory per latency CTA (caps CTAs per SM)
     int head_per_sm = 32; // PBSGPU_HYBRID_HEAD_PER_SM: chunks per SM of the long partition (and job) that may take the latency kernel
+    int mid_x10 = 0;      // PBSGPU_BULK_MID_X10: > 0: bulk chunks longer than mid_x10/10 x avg are launched on a HIGH-PRIORITY bulk
+                          // stream of their own, so the longer chains of every job in flight start before the short ones
 };
 cudaError_t launch_sha_simple(const ShaArgs &a, cudaStream_t st);
 cudaError_t launch_sha_tuned(const ShaArgs &a, const ShaTune &tune, cudaStream_t st);   // throughput kernel
 cudaError_t launch_sha_split(const ShaArgs &a, const ShaTune &tune, cudaStream_t st);   // latency kernel
 cudaError_t launch_split_point(const uint32_t *len_sorted_desc, const unsigned long long *n_chunks, uint64_t cap,
                                uint32_t threshold, unsigned long long max_head, unsigned long long *n_head,
-                               cudaStream_t st);
+                               uint32_t threshold_mid, unsigned long long *n_mid, cudaStream_t st);
 cudaError_t launch_len_keys(const ChunkRef *chunks, const unsigned long long *n_chunks, uint64_t cap,
                             uint32_t *keys, uint32_t *vals, cudaStream_t st);
 cudaError_t launch_pack_chunks(const ChunkRef *chunks, const uint8_t *digests, const uint8_t *hit,

@@ -110,6 +110,14 @@ __device__ __forceinline__ bool sha_slot(const ShaArgs &a, uint64_t t, uint64_t 
     unsigned long long head = a.part ? *a.n_head : 0ull;
     if (head > n) head = n;
     if (a.part == 1) { pos = t; return t < head; }
+    if (a.part >= 3) {
+        unsigned long long mid = *a.n_mid;
+        if (mid > n) mid = n;
+        if (mid < head) mid = head;
+        if (a.part == 3) { pos = t + head; return pos < mid; }
+        pos = t + mid;
+        return pos < n;
+    }
     pos = t + head;
     return pos < n;
 }
@@ -465,22 +473,32 @@ cudaError_t launch_sha_split(const ShaArgs &a, const ShaTune &tune, cudaStream_t
 // otherwise structured data cuts every chunk at max) only the longest ones go there and the rest stays
 // with the throughput kernel on the big partition
 __global__ void k_split_point(const uint32_t *len_sorted_desc, const unsigned long long *n_chunks, uint64_t cap,
-                              uint32_t threshold, unsigned long long max_head, unsigned long long *n_head) {
+                              uint32_t threshold, unsigned long long max_head, unsigned long long *n_head,
+                              uint32_t threshold_mid, unsigned long long *n_mid) {
     unsigned long long n = *n_chunks;
     if (n > cap) n = cap;
-    unsigned long long lo = 0, hi = n;     // first index with len <= threshold
-    while (lo < hi) {
-        unsigned long long mid = (lo + hi) >> 1;
-        if (len_sorted_desc[mid] > threshold) lo = mid + 1; else hi = mid;
-    }
-    unsigned long long h = (lo + 31) & ~31ull;
+    auto first_le = [&](uint32_t thr) {     // first index with len <= thr (lengths sorted descending)
+        unsigned long long lo = 0, hi = n;
+        while (lo < hi) {
+            unsigned long long mid = (lo + hi) >> 1;
+            if (len_sorted_desc[mid] > thr) lo = mid + 1; else hi = mid;
+        }
+        return lo;
+    };
+    unsigned long long h = (first_le(threshold) + 31) & ~31ull;
     if (h > max_head) h = max_head & ~31ull;
-    *n_head = h > n ? n : h;
+    if (h > n) h = n;
+    *n_head = h;
+    if (n_mid) {
+        unsigned long long m = (first_le(threshold_mid) + 31) & ~31ull;
+        if (m > n) m = n;
+        *n_mid = m < h ? h : m;
+    }
 }
 cudaError_t launch_split_point(const uint32_t *len_sorted_desc, const unsigned long long *n_chunks, uint64_t cap,
                                uint32_t threshold, unsigned long long max_head, unsigned long long *n_head,
-                               cudaStream_t st) {
-    k_split_point<<<1, 1, 0, st>>>(len_sorted_desc, n_chunks, cap, threshold, max_head, n_head);
+                               uint32_t threshold_mid, unsigned long long *n_mid, cudaStream_t st) {
+    k_split_point<<<1, 1, 0, st>>>(len_sorted_desc, n_chunks, cap, threshold, max_head, n_head, threshold_mid, n_mid);
     return cudaGetLastError();
 }
 

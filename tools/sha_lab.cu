@@ -184,7 +184,7 @@ template <int V, int THREADS, int MINB> static void lab(const Work &w) {
 }
 static ShaArgs sha_args(const Work &w) {
     ShaArgs a; a.base = w.buf; a.off = nullptr; a.chunks = w.refs; a.order = nullptr; a.n_chunks = w.n_dev; a.chunk_cap = w.n;
-    a.digests = w.dig; a.n_head = nullptr; a.part = 0; return a;
+    a.digests = w.dig; a.n_head = nullptr; a.n_mid = nullptr; a.part = 0; return a;
 }
 template <int M> static void prod_tuned(const Work &w) {
     pbsgpu::Opq o{1u, 1u << 29, 1u << 22, 1u << 7};
