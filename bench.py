@@ -533,6 +533,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         except Exception as ex:
             out["value_distinct"] = {"value": None, "error": repr(ex)}
         torch.cuda.empty_cache()
+    if world > 1 and os.environ.get("PBSGPU_BENCH_CLOSE_COMM_BEFORE_E2E") and comm is not None:
+        comm.close()
+        comm = None
     if not args.no_e2e:
         # every rank runs the host-buffer path on its own GPU / PCIe link (rank r hashes its own files);
         # whole-job e2e = bytes of all ranks / slowest rank's time
@@ -568,7 +571,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
-        comm.close()
+        if comm is not None:
+            comm.close()
         dist.destroy_process_group()
     eng.close()
 
