@@ -68,6 +68,22 @@ int pbsgpu_fail(pbsgpu_ctx *c, int code, const char *fmt, ...) {
     return code;
 }
 
+Guard::Guard(pbsgpu_ctx *c) : lk(c->mu) {
+    static auto getcur = pbsgpu_driver_ep<CUresult (*)(CUcontext *)>("cuCtxGetCurrent");
+    CUcontext cur = nullptr;
+    const bool known = getcur && getcur(&cur) == CUDA_SUCCESS;
+    if (known && cur == nullptr) unbind = true;                    // fresh thread: nothing to restore but "no context"
+    else if (cudaGetDevice(&prev) != cudaSuccess) { (void)cudaGetLastError(); prev = -1; }
+    if (prev == c->device) prev = -1;
+    else cudaSetDevice(c->device);
+}
+Guard::~Guard() {
+    if (unbind) {
+        static auto setcur = pbsgpu_driver_ep<CUresult (*)(CUcontext)>("cuCtxSetCurrent");
+        if (setcur) setcur(nullptr);
+    } else if (prev >= 0) cudaSetDevice(prev);
+}
+
 bool pbsgpu_is_device_ptr(const void *p) {
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { (void)cudaGetLastError(); return false; }

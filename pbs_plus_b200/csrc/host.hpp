@@ -96,16 +96,18 @@ int pbsgpu_fail(pbsgpu_ctx *c, int code, const char *fmt, ...);
         }                                                                                              \
     } while (0)
 
-// one call at a time per ctx + device binding for this OS thread (goroutines migrate); the caller's current
-// device is restored on exit so a host framework that tracks it (torch) is not retargeted behind its back
+// one call at a time per ctx + device binding for this OS thread (goroutines migrate).  The caller's binding is restored
+// on exit so a host framework that tracks the current device (torch) is not retargeted behind its back -- but ONLY a
+// binding the thread really had: a thread that never touched CUDA reports "device 0" from cudaGetDevice, and restoring
+// that with cudaSetDevice(0) would CREATE a primary context on GPU 0 in every process of a multi-GPU job (measured: the
+// e2e leg of ranks 1..7 then waits seconds for context creation on rank 0's busy GPU, profiles/r02_e2e_multirank.txt).
+// Such a thread is returned to "no context" (cuCtxSetCurrent(NULL)).
 struct Guard {
     std::lock_guard<std::recursive_mutex> lk;
-    int prev = -1;
-    explicit Guard(pbsgpu_ctx *c) : lk(c->mu) {
-        if (cudaGetDevice(&prev) != cudaSuccess) { (void)cudaGetLastError(); prev = -1; }
-        if (prev != c->device) cudaSetDevice(c->device); else prev = -1;
-    }
-    ~Guard() { if (prev >= 0) cudaSetDevice(prev); }
+    int prev = -1;        // device to restore with cudaSetDevice, or -1
+    bool unbind = false;  // the thread had no CUDA context: unbind again on exit
+    explicit Guard(pbsgpu_ctx *c);
+    ~Guard();
 };
 
 bool pbsgpu_is_device_ptr(const void *p);

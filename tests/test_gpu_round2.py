@@ -447,3 +447,22 @@ def test_calls_leave_the_callers_current_device_alone(eng, torch):
     before = torch.cuda.current_device()
     eng.sha256_batch(rnd(1000, 1), [0], [1000])
     assert torch.cuda.current_device() == before
+    # a thread that never touched CUDA must be left WITHOUT a context: "restoring" cudaGetDevice()'s default 0 would create
+    # a primary context on GPU 0 in every rank of a multi-GPU job (profiles/r02_e2e_multirank.txt)
+    try:
+        from cuda import cuda as cu
+    except Exception:
+        pytest.skip("cuda-python not importable")
+    import threading
+    seen = {}
+
+    def work():
+        cu.cuInit(0)
+        seen["before"] = int(cu.cuCtxGetCurrent()[1]) if cu.cuCtxGetCurrent()[1] is not None else 0
+        seen["digest"] = bytes(eng.sha256_batch(rnd(1000, 1), [0], [1000])[0])
+        c = cu.cuCtxGetCurrent()[1]
+        seen["after"] = int(c) if c is not None else 0
+
+    t = threading.Thread(target=work); t.start(); t.join()
+    assert seen["before"] == 0 and seen["after"] == 0, seen
+    assert seen["digest"] == hashlib.sha256(rnd(1000, 1).tobytes()).digest()

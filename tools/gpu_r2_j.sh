@@ -13,9 +13,5 @@ if m:
 else: print(sys.argv[1], 'FAILED', t[-300:], open(f"gpurun_out/r2j_{sys.argv[1]}.err").read()[-500:])
 PY
 }
-run default 29521 X=1 | tee -a gpurun_out/r2j_summary.txt
-run closecomm 29522 PBSGPU_BENCH_CLOSE_COMM_BEFORE_E2E=1 | tee -a gpurun_out/r2j_summary.txt
-B="$B --e2e-threads 1"
-run threads1 29523 X=1 | tee -a gpurun_out/r2j_summary.txt
+run fixed 29521 X=1 | tee -a gpurun_out/r2j_summary.txt
 B="bench.py --gpus 2 --steps 2 --warmup 1 --files 128 --no-cpu --no-prewarm"
-run nopart 29524 PBSGPU_PARTITION_SMS=0 | tee -a gpurun_out/r2j_summary.txt
