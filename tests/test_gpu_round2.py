@@ -427,7 +427,8 @@ def test_knobs_are_read_per_context_and_results_do_not_depend_on_them(torch):
     ref = oracle.chunk_digest_streams(oracle.config(1 << 16), arrs).tobytes()
     d = to_dev(torch, buf)
     for env in ({"PBSGPU_SHA_HYBRID": "2", "PBSGPU_PARTITION_SMS": "0"}, {"PBSGPU_SHA_MODE": "0"}, {"PBSGPU_SHA_MODE": "13"},
-                {"PBSGPU_SHA_HYBRID": "0"}, {"PBSGPU_HYBRID_THR_X10": "5"}, {"PBSGPU_CRC_VARIANT": "1"}):
+                {"PBSGPU_SHA_HYBRID": "0"}, {"PBSGPU_HYBRID_THR_X10": "5"}, {"PBSGPU_CRC_VARIANT": "1"},
+                {"PBSGPU_BULK_MID_X10": "12", "PBSGPU_HYBRID_THR_X10": "20"}, {"PBSGPU_SCAN_LANES": "1"}):
         os.environ.update(env)
         try:
             e = pg.Engine(0)
