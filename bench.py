@@ -232,10 +232,12 @@ def h2d_roofline(torch, host_arr, nbytes=8 << 30):
     return best
 
 
-def run_distinct(args, eng, pg, torch, cfg, total_gib=768, batch_files=256, nbuf=8):
+def run_distinct(args, eng, pg, torch, cfg, total_gib=768, batch_files=256, nbuf=6, early=True):
     """value_distinct: the same path over NON-REPEATING data (the cfg3 corpus): every batch is generated on the device,
-    hashed ONCE, and its buffer is refilled only after its job was collected.  Depth is bounded by HBM (nbuf x batch), not
-    by the number of steps -- the honest counterpart of the repeated-buffer headline.  A second context generates the
+    hashed ONCE, and its buffer is refilled as soon as the device no longer reads it -- with `early` (the default,
+    PBSGPU_BATCH_EARLY_INPUT) that is when the bulk pass and the copy of the long chunks into the library's arena are done,
+    without it only when the job's last 16 MiB chain ended.  Depth is bounded by HBM (nbuf x batch + arena), not by the
+    number of steps -- the honest counterpart of the repeated-buffer headline.  A second context generates the
     next batches concurrently (its kernels share the GPU with the hashing); the wall time INCLUDES that generation."""
     import queue
     import threading
@@ -268,28 +270,45 @@ def run_distinct(args, eng, pg, torch, cfg, total_gib=768, batch_files=256, nbuf
         full_q.put(None)
 
     chunks = hits = 0
-    inflight = deque()
+    pend_in, pend_out = deque(), deque()      # jobs whose input is still being read / whose records are not collected yet
+    max_jobs = max(24, 2 * nbuf)
+
+    def release_one():
+        job, slot = pend_in.popleft()
+        job.wait_input()                      # bulk pass + long-chunk gather done: the buffer can be refilled
+        free_q.put(slot)
 
     def drain():
         nonlocal chunks, hits
-        job, slot = inflight.popleft()
-        rec, _ = job.wait()
+        rec, _ = pend_out.popleft().wait()
         chunks += len(rec); hits += int((rec["flags"] & 1).sum())
-        free_q.put(slot)
 
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     th = threading.Thread(target=producer, daemon=True)
     th.start()
-    while True:
-        item = full_q.get()
-        if item is None:
-            break
-        _, slot = item
-        inflight.append((eng.submit(cfg, bufs[slot], off, ln, digest_set=known), slot))   # in corpus order: the set sees the corpus in order
-        while len(inflight) > nbuf - 2:
+    done = False
+    while not done or pend_in:
+        item = None
+        if not done:
+            try:
+                item = full_q.get(block=not pend_in)
+            except queue.Empty:
+                item = None
+            else:
+                if item is None:
+                    done = True
+        if item is not None:
+            _, slot = item
+            job = eng.submit(cfg, bufs[slot], off, ln, digest_set=known, early_input=early)   # corpus order: the set sees it in order
+            pend_in.append((job, slot)); pend_out.append(job)
+        while pend_in and pend_in[0][0].input_done():
+            release_one()
+        if pend_in and (item is None or len(pend_in) > nbuf - 2):
+            release_one()                     # nothing to submit (or the generator is out of buffers): wait for the oldest input
+        while len(pend_out) > max_jobs:
             drain()
-    while inflight:
+    while pend_out:
         drain()
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
@@ -301,7 +320,8 @@ def run_distinct(args, eng, pg, torch, cfg, total_gib=768, batch_files=256, nbuf
     if err:
         return {"value": None, "error": err[0]}
     return {"value": nbytes / wall / GIB, "unit": "GiB/s", "bytes": nbytes, "batches": n_batches,
-            "batch_GiB": batch_files * file_len / GIB, "buffers": nbuf, "chunks": chunks, "known_chunks": hits,
+            "batch_GiB": batch_files * file_len / GIB, "buffers": nbuf, "early_input": bool(early),
+            "chunks": chunks, "known_chunks": hits,
             "hit_rate": hits / max(1, chunks), "seconds": wall,
             "generation_alone_GBps": batch_files * file_len / gen_alone / 1e9,
             "generation_share_if_serial": (n_batches * gen_alone) / wall,
@@ -529,7 +549,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     torch.cuda.empty_cache()
     if world == 1 and not args.no_distinct:
         try:
-            out["value_distinct"] = run_distinct(args, eng, pg, torch, cfg, total_gib=args.distinct_gib)
+            out["value_distinct"] = run_distinct(args, eng, pg, torch, cfg, total_gib=args.distinct_gib, nbuf=args.distinct_bufs,
+                                                 batch_files=args.distinct_batch_files, early=bool(args.distinct_early))
         except Exception as ex:
             out["value_distinct"] = {"value": None, "error": repr(ex)}
         torch.cuda.empty_cache()
@@ -785,6 +806,9 @@ def main():
     ap.add_argument("--no-verify", action="store_true", help="skip the untimed post-run comparison with the oracle")
     ap.add_argument("--no-distinct", action="store_true", help="skip the non-repeating-data figure (value_distinct)")
     ap.add_argument("--distinct-gib", type=int, default=768)
+    ap.add_argument("--distinct-bufs", type=int, default=6, help="16 GiB input buffers of the value_distinct run")
+    ap.add_argument("--distinct-batch-files", type=int, default=256, help="files (of --file-mib) per batch of the value_distinct run")
+    ap.add_argument("--distinct-early", type=int, default=1, help="0: value_distinct without PBSGPU_BATCH_EARLY_INPUT")
     ap.add_argument("--total-tb", type=float, default=10.0, help="cfg3 only")
     ap.add_argument("--no-prewarm", action="store_true")
     ap.add_argument("--inflight", type=int, default=0,

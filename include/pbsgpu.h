@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PBSGPU_VERSION 200 /* 0.2.0 */
+#define PBSGPU_VERSION 201 /* 0.2.0 */
 
 /* error codes (negative errno values) */
 #define PBSGPU_OK 0
@@ -161,6 +161,19 @@ int pbsgpu_chunk_digest_batch_ex(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg, const v
                                  uint64_t cap, uint64_t *n_out);
 int pbsgpu_batch_submit_ex(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg, const void *base_dev, const uint64_t *off,
                            const uint64_t *len, uint32_t n, const pbsgpu_batch_opts *opts, pbsgpu_job **job);
+/* pbsgpu_batch_opts.flags for pbsgpu_batch_submit_ex.
+ * PBSGPU_BATCH_EARLY_INPUT: give the input buffer back BEFORE the job is done.  A batch's results wait for the serial
+ * SHA-256 chain of its longest chunk (~0.3 s for a 16 MiB chunk) -- ten times longer than the rest of a 16 GiB batch --
+ * and until then the device reads the input.  With this flag the long chunks (about 11 % of the bytes on backup data)
+ * are first copied into an arena inside the library (PBSGPU_ARENA_MB, default 32 GiB, halved until it fits; allocated on first use) and hashed
+ * from there: pbsgpu_batch_wait_input returns as soon as the bulk pass and that copy are done, the caller may overwrite
+ * or free the buffer and submit the next batch into it, and collects the records later with pbsgpu_batch_wait (in
+ * submission order when a set is shared).  pbsgpu_batch_input_done is the non-blocking form (1 free, 0 not yet).
+ * Results are identical with and without the flag; without it (or when no arena can be allocated) both calls simply
+ * report the end of the job. */
+#define PBSGPU_BATCH_EARLY_INPUT 1u
+int pbsgpu_batch_wait_input(pbsgpu_job *job);
+int pbsgpu_batch_input_done(pbsgpu_job *job);
 /* Frees a job without collecting it (after a failed wait, or to abandon it); waits for its kernels. */
 void pbsgpu_batch_free(pbsgpu_job *job);
 

@@ -21,6 +21,7 @@ class PbsGpuError(RuntimeError):
 
 
 EINVAL, ENOMEM, ERANGE, ECUDA, ENODEV, ESTATE = -22, -12, -34, -5, -19, -77
+BATCH_EARLY_INPUT = 1  # pbsgpu_batch_opts.flags
 
 
 class Cfg(C.Structure):
@@ -71,7 +72,7 @@ SYMBOLS = [
     "pbsgpu_version", "pbsgpu_open", "pbsgpu_close", "pbsgpu_strerror", "pbsgpu_device_info",
     "pbsgpu_set_profiling", "pbsgpu_partition_info", "pbsgpu_scan_partition_sms", "pbsgpu_set_kernel_variant", "pbsgpu_config", "pbsgpu_config_kib",
     "pbsgpu_default_table", "pbsgpu_chunk_digest_batch", "pbsgpu_batch_submit", "pbsgpu_batch_wait",
-    "pbsgpu_chunk_digest_batch_ex", "pbsgpu_batch_submit_ex", "pbsgpu_batch_free",
+    "pbsgpu_chunk_digest_batch_ex", "pbsgpu_batch_submit_ex", "pbsgpu_batch_free", "pbsgpu_batch_wait_input", "pbsgpu_batch_input_done",
     "pbsgpu_scan_batch", "pbsgpu_sha256_batch", "pbsgpu_stream_open", "pbsgpu_stream_write",
     "pbsgpu_stream_poll", "pbsgpu_stream_finish", "pbsgpu_stream_close", "pbsgpu_stream_reserve", "pbsgpu_stream_commit",
     "pbsgpu_stream_slot_bytes", "pbsgpu_stream_suggest", "pbsgpu_stream_position", "pbsgpu_set_create",
@@ -117,6 +118,8 @@ def lib() -> C.CDLL:
     L.pbsgpu_chunk_digest_batch_ex.argtypes = [vp, C.POINTER(Cfg), vp, vp, vp, C.c_uint32, C.POINTER(BatchOpts), vp, C.c_uint64, u64p]
     L.pbsgpu_batch_submit_ex.argtypes = [vp, C.POINTER(Cfg), vp, vp, vp, C.c_uint32, C.POINTER(BatchOpts), C.POINTER(vp)]
     L.pbsgpu_batch_free.argtypes = [vp]
+    L.pbsgpu_batch_wait_input.argtypes = [vp]
+    L.pbsgpu_batch_input_done.argtypes = [vp]
     L.pbsgpu_batch_free.restype = None
     L.pbsgpu_scan_batch.argtypes = [vp, C.POINTER(Cfg), vp, vp, vp, C.c_uint32, vp, C.c_uint64, vp, u64p]
     L.pbsgpu_sha256_batch.argtypes = [vp, vp, vp, vp, C.c_uint32, vp]

@@ -240,6 +240,9 @@ static void ctx_destroy(pbsgpu_ctx *ctx) {
     if (ctx->d_rot) cudaFree(ctx->d_rot);
     if (ctx->d_crc_tables) cudaFree(ctx->d_crc_tables);
     if (ctx->d_xxh_tab) cudaFree(ctx->d_xxh_tab);
+    for (auto &r : ctx->arena_recs) cudaEventDestroy(r.ev);
+    ctx->arena_recs.clear();
+    if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->epoch) cudaEventDestroy(ctx->epoch);
     if (ctx->g_long || ctx->g_bulk || ctx->g_scan) {
         auto gdestroy = pbsgpu_driver_ep<CUresult (*)(CUgreenCtx)>("cuGreenCtxDestroy");
@@ -288,6 +291,8 @@ extern "C" int pbsgpu_open(int device, pbsgpu_ctx **out) {
         ctx->crc_variant = env_int("PBSGPU_CRC_VARIANT", 0);
         if (getenv("PBSGPU_STREAM_WINDOW")) ctx->stream_window = strtoull(getenv("PBSGPU_STREAM_WINDOW"), nullptr, 0);
         ctx->stream_nbuf = std::max(2, std::min(32, env_int("PBSGPU_STREAM_NBUF", ctx->stream_nbuf)));
+        if (getenv("PBSGPU_ARENA_MB")) ctx->arena_want = strtoull(getenv("PBSGPU_ARENA_MB"), nullptr, 0) << 20;
+        ctx->arena_frac_x16 = std::max(1, std::min(16, env_int("PBSGPU_ARENA_FRAC_X16", ctx->arena_frac_x16)));
         int prio_lo = 0, prio_hi = 0;
         cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
         const int side_prio = env_int("PBSGPU_HYBRID_PRIO", 0) ? prio_hi : prio_lo;   // 1: long-chunk kernels on a high-priority stream
@@ -397,9 +402,9 @@ void pbsgpu_job_release(pbsgpu_job *j) {
     }
     void *devp[] = {j->d_off, j->d_len, j->d_tile_first, j->d_cand, j->d_cand_sorted, j->d_forced, j->d_counters, j->d_counts,
                     j->d_chunk_first, j->d_consumed, j->d_chunks, j->d_keys, j->d_keys2, j->d_vals, j->d_vals2,
-                    j->d_digests, j->d_hit, j->d_out, j->d_temp, j->d_set_scratch};
+                    j->d_digests, j->d_hit, j->d_out, j->d_temp, j->d_set_scratch, j->d_arena_off};
     for (void *p : devp) c->dev.put(p);
-    c->pin.put(j->h_counters); c->pin.put(j->h_out); c->pin.put(j->h_consumed);
+    c->pin.put(j->h_counters); c->pin.put(j->h_out); c->pin.put(j->h_consumed); c->pin.put(j->h_early);
     if (j->have_events) for (int i = 0; i < EV_COUNT; i++) cudaEventDestroy(j->ev[i]);
     delete j;
 }
@@ -533,6 +538,48 @@ int pbsgpu_job_create(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg, const void *base_d
     return PBSGPU_OK;
 }
 
+// Long-chunk arena: reserve a region of the ring for job `j` and make `side` (the stream its gather runs on) wait for
+// the latency kernels of the jobs that used the region before.  Returns false when no arena can be had
+// (the job then runs without early release).
+static bool arena_reserve(pbsgpu_job *j, cudaStream_t side) {
+    pbsgpu_ctx *ctx = j->ctx;
+    if (!ctx->arena && !ctx->arena_failed) {
+        uint64_t want = ctx->arena_want;
+        while (want >= (256ull << 20)) {
+            if (cudaMalloc((void **)&ctx->arena, want) == cudaSuccess) { ctx->arena_bytes = want; break; }
+            (void)cudaGetLastError();
+            ctx->arena = nullptr;
+            want >>= 1;
+        }
+        if (!ctx->arena) ctx->arena_failed = true;
+        if (getenv("PBSGPU_DEBUG")) fprintf(stderr, "pbsgpu: long-chunk arena %llu MiB\n", (unsigned long long)(ctx->arena_bytes >> 20));
+    }
+    if (!ctx->arena) return false;
+    if (!j->d_arena_off) {
+        j->max_head = (uint64_t)ctx->tune.head_per_sm * (uint64_t)(ctx->part_sms > 0 ? ctx->part_sms : 24);
+        j->d_arena_off = (uint64_t *)ctx->dev.get(sizeof(uint64_t) * (j->max_head + 32));
+        j->h_early = (unsigned long long *)ctx->pin.get(sizeof(unsigned long long));
+        if (!j->d_arena_off || !j->h_early) return false;
+    }
+    uint64_t need = j->total_bytes / 16 * (uint64_t)ctx->arena_frac_x16 + (uint64_t)j->cfg.max + 4096;
+    need = std::min((need + 255) & ~255ull, ctx->arena_bytes & ~255ull);
+    if (ctx->arena_cursor + need > ctx->arena_bytes) ctx->arena_cursor = 0;
+    const uint64_t lo = ctx->arena_cursor, hi = lo + need;
+    ctx->arena_cursor = hi;
+    for (auto it = ctx->arena_recs.begin(); it != ctx->arena_recs.end();) {
+        if (it->lo < hi && lo < it->hi) {
+            if (cudaStreamWaitEvent(side, it->ev, 0) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+            cudaEventDestroy(it->ev);
+            it = ctx->arena_recs.erase(it);
+        } else ++it;
+    }
+    cudaEvent_t ev = nullptr;
+    if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    ctx->arena_recs.push_back({lo, hi, ev});   // recorded by the caller right after the latency kernel
+    j->arena_lo = lo; j->arena_len = need;
+    return true;
+}
+
 // The hybrid SHA launch pays off when the long-chunk kernels have SMs of their own (partition); without
 // a partition their CTAs pin shared memory for ~0.3 s and starve the whole-SM scan CTAs of later batches
 // (measured: 163 vs 143 ms/step).  PBSGPU_SHA_HYBRID=2 forces it on regardless, 0 turns it off.
@@ -594,6 +641,7 @@ int pbsgpu_job_enqueue_back(pbsgpu_job *j) {
     cudaStream_t st = j->st;
     const uint32_t n = j->n;
     size_t tb = j->temp_bytes;
+    bool early = false;
     if (j->ss != st) CK(cudaStreamWaitEvent(st, j->ev[EV_RESOLVE], 0));   // the chunk list comes from the scan partition
     if (j->profiling) CK(cudaEventRecord(j->ev[EV_BACK], st));
     if (j->want_digests && j->chunk_cap) {
@@ -621,12 +669,23 @@ int pbsgpu_job_enqueue_back(pbsgpu_job *j) {
             uint32_t thr_mid = thr_mid64 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)thr_mid64;
             CK(launch_split_point(j->d_keys2, &j->d_counters[1], j->chunk_cap, thr, max_head, &j->d_counters[2], thr_mid,
                                   use_mid ? &j->d_counters[4] : nullptr, st));
+            ha.n_head = &j->d_counters[2];
+            // early input release: the head chunks are copied to the arena and hashed from there
+            // (the copy runs HERE, on the job's own stream and the big partition -- a few ms -- not on the side stream,
+            // where it would queue behind the 0.3 s latency kernel of the slot's previous job)
+            early = j->early && !serial && !use_mid && arena_reserve(j, st);
+            if (early) {
+                CK(launch_arena_plan(ha, &j->d_counters[2], j->arena_len, j->d_arena_off, st));
+                CK(launch_arena_gather(ha, ctx->arena + j->arena_lo, j->d_arena_off, ctx->sm_count, st));
+                ha.arena = ctx->arena + j->arena_lo; ha.arena_off = j->d_arena_off;
+            }
             CK(cudaEventRecord(j->ev[EV_FORK], st));
             if (!serial) CK(cudaStreamWaitEvent(side, j->ev[EV_FORK], 0));
-            ha.n_head = &j->d_counters[2];
             ha.n_mid = use_mid ? &j->d_counters[4] : nullptr;
             ha.part = 1; CK(launch_sha_split(ha, ctx->tune, side));
+            ha.arena = nullptr; ha.arena_off = nullptr;
             CK(cudaEventRecord(j->ev[EV_JOIN], side));
+            if (early) CK(cudaEventRecord(ctx->arena_recs.back().ev, side));   // the region may be reused after this
             if (use_mid) {   // the longer bulk chunks of every job in flight start first (high-priority stream), the short ones fill in
                 CK(cudaStreamWaitEvent(j->st3, j->ev[EV_FORK], 0));
                 ha.part = 3; CK(launch_sha_tuned(ha, ctx->tune, j->st3));
@@ -637,15 +696,28 @@ int pbsgpu_job_enqueue_back(pbsgpu_job *j) {
                 ha.part = 2; CK(launch_sha_tuned(ha, ctx->tune, st));
             }
             CK(cudaEventRecord(j->ev[EV_BULK], st));
-            if (!serial) CK(cudaStreamWaitEvent(st, j->ev[EV_JOIN], 0));
+            if (early) {
+                // the caller's buffer is free once the bulk pass and the gather are done -- provided the candidate buffer
+                // did not overflow (then the job is rerun from the input; pbsgpu_batch_wait_input checks the count)
+                CK(cudaMemcpyAsync(j->h_early, &j->d_counters[0], sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+                CK(cudaEventRecord(j->ev[EV_INPUT], st));
+            } else if (!serial) CK(cudaStreamWaitEvent(st, j->ev[EV_JOIN], 0));
         }
     }
-    CK(cudaEventRecord(j->ev[EV_SHA], st));
+    j->early_active = early;
     // The job's tail -- K4 (fused probe + insert), pack, D2H -- runs on the context's ONE tail stream when a set is
     // attached: jobs that share a set are thereby ordered in submission order without holding each other's streams
-    // (a job's own stream is free for the slot's next job as soon as its SHA-256 is done).
-    cudaStream_t ts = (j->set && j->want_digests) ? ctx->tail_stream : st;
-    if (ts != st) CK(cudaStreamWaitEvent(ts, j->ev[EV_SHA], 0));
+    // (a job's own stream is free for the slot's next job as soon as its SHA-256 is done).  An early-release job always
+    // takes the tail stream: its own stream must not wait ~0.3 s for the long chunks' chains.
+    cudaStream_t ts = ((j->set && j->want_digests) || early) ? ctx->tail_stream : st;
+    if (early) {
+        CK(cudaStreamWaitEvent(ts, j->ev[EV_INPUT], 0));
+        CK(cudaStreamWaitEvent(ts, j->ev[EV_JOIN], 0));
+        CK(cudaEventRecord(j->ev[EV_SHA], ts));
+    } else {
+        CK(cudaEventRecord(j->ev[EV_SHA], st));
+        if (ts != st) CK(cudaStreamWaitEvent(ts, j->ev[EV_SHA], 0));
+    }
     if (j->set && j->want_digests) {
         int rc = pbsgpu_set_enqueue_fused(j->set, j->d_digests, &j->d_counters[1], j->chunk_cap, &j->d_counters[0], j->cand_cap,
                                           j->d_hit, &j->d_counters[3], j->d_set_scratch, ts);
@@ -710,7 +782,7 @@ int pbsgpu_job_finish(pbsgpu_job *j) {
     t.scan_launches = 1;
     const bool hyb = j->variant == 0 && hybrid_for(ctx);
     t.sha_launches = j->want_digests ? (hyb ? 2 : 1) : 0;
-    t.other_launches = 3 + (j->d_forced ? 1 : 0) + (j->want_digests ? 2 + (hyb ? 1 : 0) : 0) + (j->set ? 3 : 0);
+    t.other_launches = 3 + (j->d_forced ? 1 : 0) + (j->want_digests ? 2 + (hyb ? 1 : 0) : 0) + (j->set ? 3 : 0) + (j->early_active ? 2 : 0);
     if (j->profiling) {
         cudaEventElapsedTime(&t.scan_ms, j->ev[EV_START], j->ev[EV_SCAN]);
         cudaEventElapsedTime(&t.sort_ms, j->ev[EV_SCAN], j->ev[EV_SORT]);
@@ -734,6 +806,7 @@ int pbsgpu_job_finish(pbsgpu_job *j) {
 static const pbsgpu_batch_opts NO_OPTS = {sizeof(pbsgpu_batch_opts), 0, nullptr, nullptr, nullptr, 0, nullptr};
 static int opts_ok(pbsgpu_ctx *ctx, const pbsgpu_batch_opts *o) {
     if (o && o->size != sizeof(pbsgpu_batch_opts)) return fail(ctx, PBSGPU_EINVAL, "pbsgpu_batch_opts.size = %u, expected %zu", o->size, sizeof(pbsgpu_batch_opts));
+    if (o && (o->flags & ~(uint32_t)PBSGPU_BATCH_EARLY_INPUT)) return fail(ctx, PBSGPU_EINVAL, "pbsgpu_batch_opts.flags = 0x%x: unknown bits", o->flags);
     return PBSGPU_OK;
 }
 
@@ -750,6 +823,7 @@ extern "C" int pbsgpu_batch_submit_ex(pbsgpu_ctx *ctx, const pbsgpu_cfg *cfg, co
     pbsgpu_job *j = nullptr;
     rc = pbsgpu_job_create(ctx, cfg, base_dev, off, len, n, 1, 1, o.set, o.forced_stream, o.forced_off, o.n_forced, &j);
     if (rc) return rc;
+    j->early = (o.flags & PBSGPU_BATCH_EARLY_INPUT) != 0;
     rc = pbsgpu_job_enqueue(j);
     if (rc) { pbsgpu_job_sync(j); pbsgpu_job_release(j); return rc; }
     *job = j;
@@ -777,6 +851,30 @@ extern "C" int pbsgpu_batch_wait(pbsgpu_job *j, pbsgpu_chunk *out, uint64_t cap,
     }
     pbsgpu_job_release(j);
     return rc;
+}
+
+// Early input release (PBSGPU_BATCH_EARLY_INPUT): 1 = the device no longer reads the caller's buffer, 0 = not yet.
+// A job whose candidate buffer overflowed is rerun FROM THE INPUT: it reports 0 until pbsgpu_batch_wait_input or
+// pbsgpu_batch_wait ran that rerun.
+extern "C" int pbsgpu_batch_input_done(pbsgpu_job *j) {
+    if (!j) return PBSGPU_EINVAL;
+    pbsgpu_ctx *ctx = j->ctx;
+    Guard g(ctx);
+    cudaError_t e = cudaEventQuery(j->ev[j->early_active ? EV_INPUT : EV_END]);
+    if (e == cudaErrorNotReady) { (void)cudaGetLastError(); return 0; }
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(ctx, PBSGPU_ECUDA, "cudaEventQuery -> %s", cudaGetErrorString(e)); }
+    const unsigned long long nc = j->early_active ? *j->h_early : j->h_counters[0];
+    return nc <= j->cand_cap ? 1 : 0;
+}
+extern "C" int pbsgpu_batch_wait_input(pbsgpu_job *j) {
+    if (!j) return PBSGPU_EINVAL;
+    pbsgpu_ctx *ctx = j->ctx;
+    Guard g(ctx);
+    if (j->early_active) {
+        CK(cudaEventSynchronize(j->ev[EV_INPUT]));
+        if (*j->h_early <= j->cand_cap) return PBSGPU_OK;
+    }
+    return pbsgpu_job_finish(j);   // no early release (or a rerun is due): the input is free when the job is done
 }
 
 extern "C" void pbsgpu_batch_free(pbsgpu_job *j) {

@@ -6,6 +6,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <deque>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -83,6 +84,16 @@ struct pbsgpu_ctx {
     int crc_variant = 0;                      // PBSGPU_CRC_VARIANT
     uint64_t stream_window = 2ull << 30;      // PBSGPU_STREAM_WINDOW
     int stream_nbuf = 12;                     // PBSGPU_STREAM_NBUF: windows in flight per stream
+    // long-chunk arena (PBSGPU_BATCH_EARLY_INPUT jobs): one device ring, allocated on first use.  A job reserves
+    // total x arena_frac_x16 / 16 + one maximum chunk; the region is reused once the long-chunk kernels of the jobs that
+    // held it are done (stream-ordered: the new job's side stream waits on their events, the host never blocks).
+    struct ArenaRec { uint64_t lo, hi; cudaEvent_t ev; };
+    uint8_t *arena = nullptr;
+    uint64_t arena_bytes = 0, arena_cursor = 0;
+    uint64_t arena_want = 32ull << 30;        // PBSGPU_ARENA_MB
+    int arena_frac_x16 = 3;                   // PBSGPU_ARENA_FRAC_X16
+    bool arena_failed = false;
+    std::deque<ArenaRec> arena_recs;
 };
 
 int pbsgpu_fail(pbsgpu_ctx *c, int code, const char *fmt, ...);
@@ -138,7 +149,7 @@ int pbsgpu_set_process_dev(pbsgpu_set *s, const uint8_t *d_dig, uint64_t n, int 
 // ---------------------------------------------------------------------------
 // Job: one batch of device-resident streams through K1..K4 on one CUDA stream (capi.cu)
 // ---------------------------------------------------------------------------
-enum { EV_START, EV_SCAN, EV_SORT, EV_RESOLVE, EV_SHA, EV_END, EV_FORK, EV_JOIN, EV_BULK, EV_BACK, EV_SET, EV_MID, EV_COUNT };
+enum { EV_START, EV_SCAN, EV_SORT, EV_RESOLVE, EV_SHA, EV_END, EV_FORK, EV_JOIN, EV_BULK, EV_BACK, EV_SET, EV_MID, EV_INPUT, EV_COUNT };
 
 struct pbsgpu_job {
     pbsgpu_ctx *ctx = nullptr;
@@ -162,6 +173,13 @@ struct pbsgpu_job {
     pbsgpu_chunk *d_out = nullptr;
     void *d_temp = nullptr; size_t temp_bytes = 0;
     void *d_set_scratch = nullptr;
+    // long-chunk arena (PBSGPU_BATCH_EARLY_INPUT): the head chunks are copied to ctx->arena + arena_lo, the input buffer is
+    // free at EV_INPUT (bulk pass + gather done) instead of EV_END
+    bool early = false;          // asked for
+    bool early_active = false;   // ... and in effect for the pass enqueued last (hybrid launch + arena available)
+    uint64_t arena_lo = 0, arena_len = 0, max_head = 0;
+    uint64_t *d_arena_off = nullptr;
+    unsigned long long *h_early = nullptr;   // pinned: candidate count as of EV_INPUT (overflow => the input is still needed)
     // pinned host
     unsigned long long *h_counters = nullptr;
     pbsgpu_chunk *h_out = nullptr;

@@ -86,6 +86,10 @@ struct ShaArgs {
     const unsigned long long *n_mid;     // device; end of the "mid" class (>= *n_head); NULL unless part is 3 or 4
     int part;                            // 0 = everything, 1 = head only, 2 = everything but the head,
                                          // 3 = mid class [head, mid), 4 = short class [mid, n)
+    // long-chunk arena (part 1 only; NULL = read the chunks where they lie): head chunk t was copied to
+    // arena + arena_off[t] + (its source address mod 16) by k_arena_gather
+    const uint8_t *arena = nullptr;
+    const uint64_t *arena_off = nullptr;
 };
 // per-context tuning knobs of K3 (read from the environment once per pbsgpu_open)
 struct ShaTune {
@@ -104,6 +108,11 @@ cudaError_t launch_sha_split(const ShaArgs &a, const ShaTune &tune, cudaStream_t
 cudaError_t launch_split_point(const uint32_t *len_sorted_desc, const unsigned long long *n_chunks, uint64_t cap,
                                uint32_t threshold, unsigned long long max_head, unsigned long long *n_head,
                                uint32_t threshold_mid, unsigned long long *n_mid, cudaStream_t st);
+// long-chunk arena: plan the placement of the head chunks inside a reservation of `arena_cap` bytes (trims *n_head, whole
+// groups of 32, to what fits), then copy them there
+cudaError_t launch_arena_plan(const ShaArgs &a, unsigned long long *n_head, uint64_t arena_cap, uint64_t *arena_off,
+                              cudaStream_t st);
+cudaError_t launch_arena_gather(const ShaArgs &a, uint8_t *arena, const uint64_t *arena_off, int sms, cudaStream_t st);
 cudaError_t launch_len_keys(const ChunkRef *chunks, const unsigned long long *n_chunks, uint64_t cap,
                             uint32_t *keys, uint32_t *vals, cudaStream_t st);
 cudaError_t launch_pack_chunks(const ChunkRef *chunks, const uint8_t *digests, const uint8_t *hit,

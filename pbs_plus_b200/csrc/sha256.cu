@@ -340,6 +340,7 @@ __global__ void __launch_bounds__(64) k_sha_split(ShaArgs a, Opq o) {
     ChunkRef c; c.stream = 0; c.len = 0; c.start = 0;
     if (active) { id = a.order ? a.order[t] : (uint32_t)t; c = a.chunks[id]; }
     const uint8_t *p = a.base + ((a.off && active) ? a.off[c.stream] : 0) + c.start;
+    if (a.arena && active) p = a.arena + a.arena_off[t] + ((uintptr_t)p & 15);   // the gathered copy (same alignment mod 16)
     const uint32_t nblk = c.len >> 6;
     const uint32_t nblk_max = __reduce_max_sync(0xffffffffu, nblk);
     uint32_t full[SPLIT_STAGES], empty[SPLIT_STAGES];
@@ -499,6 +500,92 @@ cudaError_t launch_split_point(const uint32_t *len_sorted_desc, const unsigned l
                                uint32_t threshold, unsigned long long max_head, unsigned long long *n_head,
                                uint32_t threshold_mid, unsigned long long *n_mid, cudaStream_t st) {
     k_split_point<<<1, 1, 0, st>>>(len_sorted_desc, n_chunks, cap, threshold, max_head, n_head, threshold_mid, n_mid);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// Long-chunk arena.  A batch's input buffer is needed until the LAST of its chunks is hashed, and the serial chain of a
+// 16 MiB chunk takes ~0.3 s -- ten times longer than everything else of a 16 GiB batch.  With an arena the head chunks
+// (the ~11 % of the bytes that take the latency kernel) are copied aside first, the latency kernel reads the copy, and
+// the caller gets its buffer back as soon as the bulk pass and this copy are done.
+// Placement: slot t starts 128 B aligned and keeps the source's misalignment mod 16, so the gather is a plain uint4 copy
+// of the 16-byte vectors that cover the chunk (the same vectors the producer warp would have loaded in place).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t arena_slot_bytes(const uint8_t *p, uint32_t len) {
+    return (((uintptr_t)p & 15) + (uint64_t)len + 127) & ~127ull;
+}
+__global__ void __launch_bounds__(1024) k_arena_plan(ShaArgs a, unsigned long long *n_head, uint64_t arena_cap, uint64_t *arena_off) {
+    __shared__ uint64_t warp_sum[32];
+    __shared__ uint64_t carry_s;
+    __shared__ unsigned long long fit_s;
+    unsigned long long n = *a.n_chunks;
+    if (n > a.chunk_cap) n = a.chunk_cap;
+    unsigned long long head = *n_head;
+    if (head > n) head = n;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { carry_s = 0; fit_s = head; }
+    __syncthreads();
+    for (unsigned long long t0 = 0; t0 < head; t0 += 1024) {
+        const unsigned long long t = t0 + threadIdx.x;
+        uint64_t need = 0;
+        if (t < head) {
+            const uint32_t id = a.order ? a.order[t] : (uint32_t)t;
+            const ChunkRef c = a.chunks[id];
+            need = arena_slot_bytes(a.base + (a.off ? a.off[c.stream] : 0) + c.start, c.len);
+        }
+        uint64_t v = need;   // inclusive scan over the block
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint64_t u = __shfl_up_sync(0xffffffffu, v, d); if (lane >= (uint32_t)d) v += u; }
+        if (lane == 31) warp_sum[warp] = v;
+        const uint64_t carry = carry_s;
+        __syncthreads();
+        if (warp == 0) {
+            uint64_t w = warp_sum[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint64_t u = __shfl_up_sync(0xffffffffu, w, d); if (lane >= (uint32_t)d) w += u; }
+            warp_sum[lane] = w;
+        }
+        __syncthreads();
+        const uint64_t incl = carry + v + (warp ? warp_sum[warp - 1] : 0);
+        if (t < head) {
+            if (incl <= arena_cap) arena_off[t] = incl - need;
+            else atomicMin(&fit_s, t);
+        }
+        if (threadIdx.x == 1023) carry_s = incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && fit_s < head) *n_head = fit_s & ~31ull;   // whole latency CTAs; the rest stays with the throughput kernel
+}
+cudaError_t launch_arena_plan(const ShaArgs &a, unsigned long long *n_head, uint64_t arena_cap, uint64_t *arena_off,
+                              cudaStream_t st) {
+    k_arena_plan<<<1, 1024, 0, st>>>(a, n_head, arena_cap, arena_off);
+    return cudaGetLastError();
+}
+__global__ void __launch_bounds__(256) k_arena_gather(ShaArgs a, uint8_t *arena, const uint64_t *arena_off) {
+    unsigned long long n = *a.n_chunks;
+    if (n > a.chunk_cap) n = a.chunk_cap;
+    unsigned long long head = *a.n_head;
+    if (head > n) head = n;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (unsigned long long t = 0; t < head; t++) {
+        const uint32_t id = a.order ? a.order[t] : (uint32_t)t;
+        const ChunkRef c = a.chunks[id];
+        const uint8_t *p = a.base + (a.off ? a.off[c.stream] : 0) + c.start;
+        const uint32_t delta = (uint32_t)((uintptr_t)p & 15);
+        const uint4 *src = (const uint4 *)(p - delta);
+        uint4 *dst = (uint4 *)(arena + arena_off[t]);
+        const uint64_t nvec = ((uint64_t)delta + c.len + 15) >> 4;
+        uint64_t v = tid;
+        for (; v + 3 * stride < nvec; v += 4 * stride) {
+            const uint4 x0 = __ldcs(src + v), x1 = __ldcs(src + v + stride), x2 = __ldcs(src + v + 2 * stride), x3 = __ldcs(src + v + 3 * stride);
+            dst[v] = x0; dst[v + stride] = x1; dst[v + 2 * stride] = x2; dst[v + 3 * stride] = x3;
+        }
+        for (; v < nvec; v += stride) dst[v] = __ldcs(src + v);
+    }
+}
+cudaError_t launch_arena_gather(const ShaArgs &a, uint8_t *arena, const uint64_t *arena_off, int sms, cudaStream_t st) {
+    if (a.chunk_cap == 0) return cudaSuccess;
+    k_arena_gather<<<(unsigned)(sms > 0 ? sms : 148) * 4, 256, 0, st>>>(a, arena, arena_off);
     return cudaGetLastError();
 }
 

@@ -183,12 +183,17 @@ class Engine:
             buf[int(o): int(o) + len(a)] = a
         return self.chunk_digest_batch(cfg, buf, offs, lens, digest_set)
 
-    def submit(self, cfg: Cfg, base_dev, off, length, digest_set: "DigestSet | None" = None, forced=None) -> "Job":
+    def submit(self, cfg: Cfg, base_dev, off, length, digest_set: "DigestSet | None" = None, forced=None,
+               early_input: bool = False) -> "Job":
         """Asynchronous form; with `digest_set` the probe + insert runs as kernels on the job's stream (jobs sharing a
-        set are ordered in submission order) and the KNOWN flags come back with the records."""
+        set are ordered in submission order) and the KNOWN flags come back with the records.  `early_input`
+        (PBSGPU_BATCH_EARLY_INPUT): the long chunks are copied aside so that Job.wait_input() gives the buffer back
+        long before the records are ready."""
         o, l = self._offlen(off, length)
         h = C.c_void_p()
         opts, _k = self._opts(digest_set, forced)
+        if early_input:
+            opts.flags |= _lib.BATCH_EARLY_INPUT
         self._ck(self._L.pbsgpu_batch_submit_ex(self._h, C.byref(cfg), _ptr(base_dev), o.ctypes.data, l.ctypes.data,
                                                 len(o), C.byref(opts), C.byref(h)))
         return Job(self, h, self._chunk_cap(cfg, l) + (len(forced[0]) if forced is not None else 0), base_dev)
@@ -319,6 +324,18 @@ class Job:
         self._eng._ck(rc)
         self._keep = None
         return out[: n_out.value], t.as_dict()
+
+    def wait_input(self):
+        """Blocks until the device no longer reads the input buffer (pbsgpu_batch_wait_input); the job stays in flight."""
+        self._eng._ck(self._eng._L.pbsgpu_batch_wait_input(self._h))
+        self._keep = None
+
+    def input_done(self) -> bool:
+        """Non-blocking form of wait_input."""
+        rc = self._eng._L.pbsgpu_batch_input_done(self._h)
+        if rc < 0:
+            self._eng._ck(rc)
+        return rc == 1
 
     def free(self):
         """Abandon the job (pbsgpu_batch_free)."""

@@ -22,7 +22,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     for s in declared:
         assert hasattr(L, s), s
-    assert L.pbsgpu_version() == 200
+    assert L.pbsgpu_version() == 201
 
 
 def test_config_matches_oracle_and_rejects_bad_sizes():
@@ -96,4 +96,4 @@ int main(void) {
     subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Werror", "-I", str(ROOT / "include"), "-o", str(exe), str(src),
                            f"-L{lib}", "-lpbsgpu", f"-Wl,-rpath,{lib}"])
     out = subprocess.run([str(exe)], capture_output=True, text=True)
-    assert out.returncode == 0 and out.stdout.strip() == "version 200", (out.returncode, out.stdout, out.stderr)
+    assert out.returncode == 0 and out.stdout.strip() == "version 201", (out.returncode, out.stdout, out.stderr)
