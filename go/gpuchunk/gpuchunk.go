@@ -509,3 +509,32 @@ func (b *Batch) BlobEncode(off, length []uint64) ([][]byte, error) {
 	}
 	return res, nil
 }
+
+// BlobEncodeZ is BlobEncode with the zstd-compressed DataBlob form where that is smaller (upstream DataBlob::encode
+// keeps a compressed payload only then).  The frames are built on the GPU from RLE and raw blocks -- they remove
+// the zero runs of disk images and sparse files; data without such runs stays uncompressed.
+func (b *Batch) BlobEncodeZ(off, length []uint64) ([][]byte, error) {
+	n := len(off)
+	if n == 0 {
+		return nil, nil
+	}
+	o := make([]C.uint64_t, n)
+	l := make([]C.uint64_t, n)
+	oo := make([]C.uint64_t, n)
+	ol := make([]C.uint64_t, n)
+	var total uint64
+	for i := range off {
+		o[i], l[i], oo[i] = C.uint64_t(off[i]), C.uint64_t(length[i]), C.uint64_t(total)
+		total += uint64(C.pbsgpu_blob_size(C.uint64_t(length[i])))
+	}
+	out := make([]byte, total+1)
+	rc := C.pbsgpu_blob_encode_batch_z(b.e.ctx, b.buf, &o[0], &l[0], C.uint32_t(n), (*C.uint8_t)(unsafe.Pointer(&out[0])), &oo[0], &ol[0], nil)
+	if err := b.e.err(rc); err != nil {
+		return nil, err
+	}
+	res := make([][]byte, n)
+	for i := range off {
+		res[i] = out[uint64(oo[i]) : uint64(oo[i])+uint64(ol[i])]
+	}
+	return res, nil
+}

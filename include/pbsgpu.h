@@ -262,8 +262,7 @@ int pbsgpu_didx_parse(pbsgpu_ctx *ctx, const uint8_t *didx, uint64_t size, uint6
  * A new chunk is uploaded as a PBS DataBlob { magic[8], crc32 LE of the payload, payload } (upstream
  * pbs-datastore data_blob.rs; POST /dynamic_chunk, reference internal/server/backup/log_cleanup.go:19-31).
  * pbsgpu_crc32_batch computes zlib-compatible CRC-32s of n byte ranges (HOST or DEVICE base) on the GPU;
- * pbsgpu_blob_header fills the 12-byte header of an unencrypted, uncompressed blob.  zstd-compressed
- * blobs are out of scope. */
+ * pbsgpu_blob_header fills the 12-byte header of an unencrypted, uncompressed blob. */
 int pbsgpu_crc32_batch(pbsgpu_ctx *ctx, const void *base, const uint64_t *off, const uint64_t *len, uint32_t n,
                        uint32_t *crc_out);
 void pbsgpu_blob_header(uint32_t crc, uint8_t out[12]);
@@ -273,6 +272,15 @@ void pbsgpu_blob_header(uint32_t crc, uint8_t out[12]);
 uint64_t pbsgpu_blob_size(uint64_t payload_len);
 int pbsgpu_blob_encode_batch(pbsgpu_ctx *ctx, const void *base, const uint64_t *off, const uint64_t *len, uint32_t n,
                              uint8_t *out, const uint64_t *out_off, uint32_t *crc_out);
+/* The same with the COMPRESSED form where it is smaller (upstream `DataBlob::encode` keeps a zstd payload only then):
+ * blob i = { compressed-blob magic, crc32 LE of the frame, zstd frame } or the uncompressed blob as above; out_len[i]
+ * receives its size (<= pbsgpu_blob_size(len[i]), which is what the caller reserves at out_off[i]).  The frame is a
+ * standard zstd frame (RFC 8878) built on the device from RLE_Blocks -- 128 KiB blocks that are one repeated byte, i.e.
+ * the zero runs of disk images and sparse files -- and Raw_Blocks; there is NO match / entropy stage, so data without
+ * such runs stays uncompressed.  Any zstd decoder reads the result; it is not byte-identical to libzstd's output for the
+ * same input (no two zstd encoders are). */
+int pbsgpu_blob_encode_batch_z(pbsgpu_ctx *ctx, const void *base, const uint64_t *off, const uint64_t *len, uint32_t n,
+                               uint8_t *out, const uint64_t *out_off, uint64_t *out_len, uint32_t *crc_out);
 
 /* ---- f2 ("next" row): the commit walk's per-file content hash ----------------------------------
  * emitBackedFile tees every new file through `xxh3.New()` and keeps `h.Sum64()` (reference

@@ -111,3 +111,39 @@ def didx_build(lengths, digests, uuid: bytes = b"\0" * 16, ctime: int = 0) -> by
     hdr[24:32] = int(ctime).to_bytes(8, "little", signed=True)
     hdr[32:64] = hashlib.sha256(bytes(body)).digest()
     return bytes(hdr) + bytes(body)
+
+
+# -- f3: DataBlobs (upstream pbs-datastore data_blob.rs / file_formats.rs, restated; the magics are
+#    sha256("Proxmox Backup uncompressed blob v1.0")[:8] and sha256("Proxmox Backup zstd compressed blob v1.0")[:8],
+#    which tests/test_oracle.py re-derives) -----------------------------------------------------------
+BLOB_MAGIC_UNCOMPRESSED = bytes([66, 171, 56, 7, 190, 131, 112, 161])
+BLOB_MAGIC_COMPRESSED = bytes([49, 185, 88, 66, 111, 182, 163, 127])
+ZFRAME_BLOCK = 128 * 1024
+
+
+def zstd_frame_rle_raw(data: bytes) -> bytes:
+    """A standard zstd frame (RFC 8878 3.1.1) without match / entropy stages: Frame_Header = magic 0xFD2FB528 LE,
+    descriptor 0xE0 (8-byte Frame_Content_Size, Single_Segment), content size; then one block per 128 KiB of input --
+    an RLE_Block (type 1, Block_Size = repeat count, 1 byte) when the block is one repeated byte, else a Raw_Block
+    (type 0).  Block_Header = Last_Block | type << 1 | Block_Size << 3, 3 bytes LE.  Empty input: one empty raw block."""
+    data = bytes(data)
+    out = bytearray(b"\x28\xb5\x2f\xfd\xe0" + len(data).to_bytes(8, "little"))
+    nb = max(1, (len(data) + ZFRAME_BLOCK - 1) // ZFRAME_BLOCK)
+    for b in range(nb):
+        blk = data[b * ZFRAME_BLOCK:(b + 1) * ZFRAME_BLOCK]
+        rle = len(blk) > 0 and blk.count(blk[:1]) == len(blk)
+        hdr = int(b + 1 == nb) | ((1 if rle else 0) << 1) | (len(blk) << 3)
+        out += hdr.to_bytes(3, "little") + (blk[:1] if rle else blk)
+    return bytes(out)
+
+
+def blob_encode(data: bytes, compress: bool = True) -> bytes:
+    """DataBlob { magic[8], crc32 LE over the payload, payload }; the zstd payload only when it is smaller than the raw
+    bytes (upstream `DataBlob::encode`)."""
+    import zlib
+    data = bytes(data)
+    if compress and data:
+        fr = zstd_frame_rle_raw(data)
+        if len(fr) < len(data):
+            return BLOB_MAGIC_COMPRESSED + zlib.crc32(fr).to_bytes(4, "little") + fr
+    return BLOB_MAGIC_UNCOMPRESSED + zlib.crc32(data).to_bytes(4, "little") + data

@@ -162,6 +162,136 @@ extern "C" int pbsgpu_blob_encode_batch(pbsgpu_ctx *ctx, const void *base, const
     return PBSGPU_OK;
 }
 
+// f3, compressed form: DataBlobs whose payload is a zstd frame when that is smaller than the raw bytes (upstream
+// `DataBlob::encode` keeps the compressed form only then).  The frame is built on the device from RLE_Blocks (128 KiB
+// blocks of one repeated byte) and Raw_Blocks (zframe.cu) -- no match / entropy stage; the CRC (K6) covers the frame.
+static const uint8_t BLOB_MAGIC_COMPRESSED[8] = {49, 185, 88, 66, 111, 182, 163, 127};
+
+extern "C" int pbsgpu_blob_encode_batch_z(pbsgpu_ctx *ctx, const void *base, const uint64_t *off, const uint64_t *len, uint32_t n,
+                                          uint8_t *out, const uint64_t *out_off, uint64_t *out_len, uint32_t *crc_out) {
+    if (!ctx || (n && (!off || !len || !out || !out_off || !out_len || !base))) return PBSGPU_EINVAL;
+    Guard g(ctx);
+    if (n == 0) return PBSGPU_OK;
+    cudaStream_t st = ctx->streams[0];
+    uint64_t hi = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        if (len[i] >= (1ull << 40)) return fail(ctx, PBSGPU_EINVAL, "blob %u longer than 2^40 bytes", i);
+        hi = std::max(hi, off[i] + len[i]);
+    }
+    const bool on_dev = !hi || pbsgpu_is_device_ptr(base);
+    Scoped staged(ctx->dev, on_dev ? 0 : hi + 16);
+    if (!staged) return fail(ctx, PBSGPU_ENOMEM, "staging of %llu bytes failed", (unsigned long long)hi);
+    const uint8_t *dbase = on_dev ? (const uint8_t *)base : staged.as<uint8_t>();
+    if (!on_dev) CK(cudaMemcpyAsync(staged.p, base, hi, cudaMemcpyHostToDevice, st));
+    // K8a: which 128 KiB blocks are one repeated byte
+    std::vector<uint64_t> blk_first(n + 1);
+    uint64_t n_blocks = 0;
+    for (uint32_t i = 0; i < n; i++) { blk_first[i] = n_blocks; n_blocks += (len[i] + ZFRAME_BLOCK - 1) / ZFRAME_BLOCK; }
+    blk_first[n] = n_blocks;
+    if (n_blocks >= (1ull << 31)) return fail(ctx, PBSGPU_EINVAL, "too many 128 KiB blocks in one call (%llu)", (unsigned long long)n_blocks);
+    std::vector<uint32_t> flags(n_blocks);
+    {
+        Scoped d_off(ctx->dev, n * 8), d_len(ctx->dev, n * 8), d_first(ctx->dev, (n + 1) * 8), d_flags(ctx->dev, (n_blocks + 1) * 4);
+        if (!d_off || !d_len || !d_first || !d_flags) return fail(ctx, PBSGPU_ENOMEM, "device allocation failed");
+        cudaError_t e = cudaMemcpyAsync(d_off.p, off, n * 8, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_len.p, len, n * 8, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_first.p, blk_first.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = launch_zblock_scan(dbase, d_off.as<uint64_t>(), d_len.as<uint64_t>(), d_first.as<uint64_t>(), n, n_blocks, d_flags.as<uint32_t>(), st);
+        if (e == cudaSuccess && n_blocks) e = cudaMemcpyAsync(flags.data(), d_flags.p, n_blocks * 4, cudaMemcpyDeviceToHost, st);
+        cudaError_t es = cudaStreamSynchronize(st);
+        if (e == cudaSuccess) e = es;
+        if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(ctx, PBSGPU_ECUDA, "zstd block scan: %s", cudaGetErrorString(e)); }
+    }
+    // frame sizes; the chunks that come out smaller get a place in the stage and one emit entry per block
+    std::vector<uint8_t> comp(n, 0);
+    std::vector<uint64_t> frame_len(n, 0), frame_off, content, e_src, e_dst;
+    std::vector<uint32_t> e_hdr, comp_idx;
+    uint64_t cursor = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        const uint64_t nb = blk_first[i + 1] - blk_first[i];
+        uint64_t fl = ZFRAME_HEADER;
+        for (uint64_t b = 0; b < nb; b++) {
+            const uint64_t size = std::min<uint64_t>(ZFRAME_BLOCK, len[i] - b * ZFRAME_BLOCK);
+            fl += 3 + ((flags[blk_first[i] + b] & 0x100u) ? 1 : size);
+        }
+        frame_len[i] = fl;
+        if (len[i] == 0 || fl >= len[i]) continue;
+        comp[i] = 1;
+        comp_idx.push_back(i);
+        frame_off.push_back(cursor);
+        content.push_back(len[i]);
+        uint64_t pos = cursor + ZFRAME_HEADER;
+        for (uint64_t b = 0; b < nb; b++) {
+            const uint64_t size = std::min<uint64_t>(ZFRAME_BLOCK, len[i] - b * ZFRAME_BLOCK);
+            const uint32_t f = flags[blk_first[i] + b];
+            const bool rle = (f & 0x100u) != 0;
+            e_src.push_back(off[i] + b * ZFRAME_BLOCK);
+            e_dst.push_back(pos);
+            e_hdr.push_back((uint32_t)(b + 1 == nb) | ((rle ? 1u : 0u) << 1) | ((uint32_t)size << 3) | ((f & 0xFFu) << 24));
+            pos += 3 + (rle ? 1 : size);
+        }
+        cursor = (pos + 15) & ~15ull;
+    }
+    const uint32_t nc = (uint32_t)comp_idx.size();
+    Scoped stage(ctx->dev, nc ? cursor + 16 : 0);
+    if (!stage) return fail(ctx, PBSGPU_ENOMEM, "frame staging of %llu bytes failed", (unsigned long long)cursor);
+    std::vector<uint32_t> crc(n, 0);
+    if (nc) {
+        const uint64_t ne = e_hdr.size();
+        Scoped d_src(ctx->dev, ne * 8), d_dst(ctx->dev, ne * 8), d_hdr(ctx->dev, ne * 4), d_foff(ctx->dev, nc * 8), d_clen(ctx->dev, nc * 8);
+        if (!d_src || !d_dst || !d_hdr || !d_foff || !d_clen) return fail(ctx, PBSGPU_ENOMEM, "device allocation failed");
+        cudaError_t e = cudaMemcpyAsync(d_src.p, e_src.data(), ne * 8, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_dst.p, e_dst.data(), ne * 8, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_hdr.p, e_hdr.data(), ne * 4, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_foff.p, frame_off.data(), nc * 8, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_clen.p, content.data(), nc * 8, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = launch_zframe_hdr(stage.as<uint8_t>(), d_foff.as<uint64_t>(), d_clen.as<uint64_t>(), nc, st);
+        if (e == cudaSuccess) e = launch_zframe_emit(dbase, stage.as<uint8_t>(), d_src.as<uint64_t>(), d_dst.as<uint64_t>(), d_hdr.as<uint32_t>(), ne, st);
+        cudaError_t es = cudaStreamSynchronize(st);
+        if (e == cudaSuccess) e = es;
+        if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(ctx, PBSGPU_ECUDA, "zstd frame emit: %s", cudaGetErrorString(e)); }
+        // CRC over the frames
+        std::vector<uint64_t> flen(nc);
+        std::vector<uint32_t> fcrc(nc);
+        for (uint32_t k = 0; k < nc; k++) flen[k] = frame_len[comp_idx[k]];
+        int rc = pbsgpu_crc32_batch(ctx, stage.p, frame_off.data(), flen.data(), nc, fcrc.data());
+        if (rc) return rc;
+        for (uint32_t k = 0; k < nc; k++) crc[comp_idx[k]] = fcrc[k];
+    }
+    if (nc < n) {   // CRC over the raw payloads of the rest
+        std::vector<uint64_t> roff, rlen;
+        std::vector<uint32_t> ridx;
+        for (uint32_t i = 0; i < n; i++) if (!comp[i]) { ridx.push_back(i); roff.push_back(off[i]); rlen.push_back(len[i]); }
+        std::vector<uint32_t> rcrc(ridx.size());
+        int rc = pbsgpu_crc32_batch(ctx, hi ? (const void *)dbase : base, roff.data(), rlen.data(), (uint32_t)ridx.size(), rcrc.data());
+        if (rc) return rc;
+        for (size_t k = 0; k < ridx.size(); k++) crc[ridx[k]] = rcrc[k];
+    }
+    // assemble in the caller's memory
+    cudaStream_t cs = ctx->copy_stream;
+    uint32_t k = 0;
+    cudaError_t e = cudaSuccess;
+    for (uint32_t i = 0; i < n && e == cudaSuccess; i++) {
+        uint8_t *b = out + out_off[i];
+        memcpy(b, comp[i] ? BLOB_MAGIC_COMPRESSED : BLOB_MAGIC_UNCOMPRESSED, 8);
+        for (int q = 0; q < 4; q++) b[8 + q] = (uint8_t)(crc[i] >> (8 * q));
+        if (comp[i]) {
+            e = cudaMemcpyAsync(b + 12, stage.as<uint8_t>() + frame_off[k++], frame_len[i], cudaMemcpyDeviceToHost, cs);
+            out_len[i] = 12 + frame_len[i];
+        } else {
+            out_len[i] = 12 + len[i];
+            if (!len[i]) continue;
+            if (on_dev) e = cudaMemcpyAsync(b + 12, (const uint8_t *)base + off[i], len[i], cudaMemcpyDeviceToHost, cs);
+            else memcpy(b + 12, (const uint8_t *)base + off[i], len[i]);
+        }
+    }
+    cudaError_t es = cudaStreamSynchronize(cs);
+    if (e == cudaSuccess) e = es;
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(ctx, PBSGPU_ECUDA, "blob assembly copy: %s", cudaGetErrorString(e)); }
+    if (crc_out) memcpy(crc_out, crc.data(), (size_t)n * 4);
+    return PBSGPU_OK;
+}
+
 // ---------------------------------------------------------------------------
 // f2: XXH3-64 of n byte ranges (the commit walk's per-file content hash, commit.go:717-725, :957-976).
 // Blocks are hashed in passes of at most PBSGPU_XXH3_CAP_BLOCKS (default 8 Mi = 8 GiB of input, 512 MiB

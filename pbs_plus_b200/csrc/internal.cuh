@@ -118,6 +118,15 @@ cudaError_t launch_len_keys(const ChunkRef *chunks, const unsigned long long *n_
 cudaError_t launch_pack_chunks(const ChunkRef *chunks, const uint8_t *digests, const uint8_t *hit,
                                const unsigned long long *n_chunks, uint64_t cap, pbsgpu_chunk *out, cudaStream_t st);
 
+// ---- f3: zstd framing of constant runs (zframe.cu) ---------------------------------------
+constexpr uint32_t ZFRAME_BLOCK = 128u * 1024u;   // Block_Maximum_Size
+constexpr uint32_t ZFRAME_HEADER = 13;            // magic 4 + descriptor 1 + content size 8
+cudaError_t launch_zblock_scan(const uint8_t *base, const uint64_t *off, const uint64_t *len, const uint64_t *blk_first,
+                               uint32_t n, uint64_t n_blocks, uint32_t *flags, cudaStream_t st);
+cudaError_t launch_zframe_emit(const uint8_t *base, uint8_t *stage, const uint64_t *src_off, const uint64_t *dst_off,
+                               const uint32_t *hdr, uint64_t n_entries, cudaStream_t st);
+cudaError_t launch_zframe_hdr(uint8_t *stage, const uint64_t *frame_off, const uint64_t *content_len, uint32_t n, cudaStream_t st);
+
 // ---- digest set (K4) ----------------------------------------------------------------
 struct SetTable {
     uint64_t *tags;     // [cap] 0 = empty

@@ -245,6 +245,20 @@ class Engine:
                                                   out.ctypes.data if len(out) else None, boff.ctypes.data, crc.ctypes.data))
         return out, boff, crc
 
+    def blob_encode_batch_z(self, base, off, length):
+        """DataBlobs with a zstd payload where that is smaller (RLE / raw block frames, pbsgpu_blob_encode_batch_z)
+        -> list of n `bytes` blobs, crc[n]."""
+        o, l = self._offlen(off, length)
+        sizes = l + np.uint64(12)
+        boff = np.zeros(len(o) + 1, dtype=np.uint64)
+        np.cumsum(sizes, out=boff[1:])
+        out = np.zeros(max(1, int(boff[-1])), dtype=np.uint8)
+        blen = np.zeros(len(o), dtype=np.uint64)
+        crc = np.zeros(len(o), dtype=np.uint32)
+        self._ck(self._L.pbsgpu_blob_encode_batch_z(self._h, _ptr(base), o.ctypes.data, l.ctypes.data, len(o),
+                                                    out.ctypes.data, boff.ctypes.data, blen.ctypes.data, crc.ctypes.data))
+        return [out[int(boff[i]): int(boff[i]) + int(blen[i])].tobytes() for i in range(len(o))], crc
+
     def blob_header(self, crc: int) -> bytes:
         out = np.zeros(12, dtype=np.uint8)
         self._L.pbsgpu_blob_header(int(crc), out.ctypes.data)

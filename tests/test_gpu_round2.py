@@ -473,6 +473,62 @@ def test_blob_encode_batch_builds_complete_datablobs(eng, torch):
             assert blob[12:] == payload
 
 
+def _zstd_decode(frame: bytes, size: int) -> bytes:
+    pa = pytest.importorskip("pyarrow")
+    return pa.Codec("zstd").decompress(frame, decompressed_size=size).to_pybytes() if size else b""
+
+
+def test_blob_encode_batch_z_builds_zstd_frames_of_constant_runs(eng, torch):
+    """f3 compressed form: bit-exact against the restated framing (oracle/pyref.py), and every compressed payload is
+    decoded by libzstd (pyarrow's codec) back to the chunk.  Zero runs, non-zero runs, runs that do not line up with the
+    128 KiB block grid, ragged tails, tiny and empty chunks, unaligned sources."""
+    from oracle import pyref
+    B = 128 * 1024
+    parts = [np.zeros(4 << 20, np.uint8),                                  # a zero chunk of a disk image
+             rnd(1_000_000, 70),                                           # incompressible
+             np.concatenate([rnd(B, 71), np.zeros(2 * B, np.uint8), rnd(5, 72)]),   # mixed, run on the block grid
+             np.concatenate([rnd(1000, 73), np.zeros(3 * B, np.uint8), rnd(B - 1000 + 77, 74)]),   # run off the grid: 2 full blocks
+             np.full(B + 1, 7, np.uint8),                                  # non-zero byte, 1-byte last block
+             np.full(20, 0x41, np.uint8), np.full(16, 0x41, np.uint8),     # 17-byte frame: smaller than 20, not than 16
+             np.zeros(0, np.uint8), rnd(1, 75),
+             np.concatenate([np.zeros(B, np.uint8), np.ones(1, np.uint8), np.zeros(B - 1, np.uint8)])]   # second block not constant
+    buf, off, ln = pack(parts, align=1)
+    off = off + np.uint64(3)                                                # every source misaligned
+    buf = np.concatenate([np.full(3, 0xEE, np.uint8), buf])
+    want = [pyref.blob_encode(p.tobytes()) for p in parts]
+    n_comp = 0
+    for base in (buf, to_dev(torch, buf)):
+        blobs, crc = eng.blob_encode_batch_z(base, off, ln)
+        for i, (blob, p) in enumerate(zip(blobs, parts)):
+            assert blob == want[i], (i, len(blob), len(want[i]))
+            assert int.from_bytes(blob[8:12], "little") == zlib.crc32(blob[12:]) == int(crc[i])
+            if blob[:8] == pyref.BLOB_MAGIC_COMPRESSED:
+                n_comp += 1
+                assert len(blob) < 12 + len(p) and _zstd_decode(blob[12:], len(p)) == p.tobytes()
+            else:
+                assert blob[:8] == pyref.BLOB_MAGIC_UNCOMPRESSED and blob[12:] == p.tobytes()
+    assert n_comp == 2 * 6
+
+
+def test_blob_encode_batch_z_on_chunker_output(eng, torch):
+    """The call as the commit walk would make it: the NEW chunks of a batch over a sparse disk image."""
+    from oracle import pyref
+    img = rnd(24 << 20, 80)
+    img[3 << 20: 11 << 20] = 0
+    img[(17 << 20) + 12345: (20 << 20) + 999] = 0
+    d = to_dev(torch, img)
+    rec = eng.chunk_digest_batch(pg.make_config(1 << 20), d, [0], [len(img)])
+    ends = rec["end_off"].astype(np.uint64)
+    starts = np.concatenate([[0], ends[:-1]]).astype(np.uint64)
+    blobs, _ = eng.blob_encode_batch_z(d, starts, ends - starts)
+    total = 0
+    for s0, e0, blob in zip(starts, ends, blobs):
+        chunk = img[int(s0): int(e0)].tobytes()
+        assert blob == pyref.blob_encode(chunk)
+        total += len(blob)
+    assert total < len(img) * 0.6                     # ~11 of 24 MiB are zero runs
+
+
 # ---- e: the NCCL merge through the C ABI ------------------------------------------------------------------------------
 def test_set_allgather_single_rank_equals_insert(eng):
     """World of one: pbsgpu_set_allgather must behave exactly like pbsgpu_set_insert (also proves that libnccl resolves

@@ -307,3 +307,28 @@ def test_xxh3_64_matches_the_libxxhash_golden_vectors():
         assert oracle.xxh3_64(data) == want, r
         n += 1
     assert n >= 90
+
+
+def test_format_magics_are_the_sha256_prefixes_upstream_derives_them_from():
+    """file_formats.rs defines every magic as sha256(<label>)[0..8]; re-deriving them pins the restated constants."""
+    assert pyref.BLOB_MAGIC_UNCOMPRESSED == hashlib.sha256(b"Proxmox Backup uncompressed blob v1.0").digest()[:8]
+    assert pyref.BLOB_MAGIC_COMPRESSED == hashlib.sha256(b"Proxmox Backup zstd compressed blob v1.0").digest()[:8]
+    assert pyref.DIDX_MAGIC == hashlib.sha256(b"Proxmox Backup dynamic sized chunk index v1.0").digest()[:8]
+
+
+def test_restated_zstd_framing_is_read_by_libzstd():
+    """oracle/pyref.zstd_frame_rle_raw against an independent decoder (pyarrow links libzstd)."""
+    pa = pytest.importorskip("pyarrow")
+    codec = pa.Codec("zstd")
+    rng = np.random.default_rng(1)
+    B = pyref.ZFRAME_BLOCK
+    cases = [b"a" * 20, b"\0" * (4 << 20), rng.integers(0, 256, 300_000, dtype=np.uint8).tobytes(), b"\0" * B + b"x",
+             b"\x07" * (B + 1), rng.integers(0, 256, B, dtype=np.uint8).tobytes() + b"\0" * (2 * B) + b"tail!"]
+    for d in cases:
+        fr = pyref.zstd_frame_rle_raw(d)
+        assert codec.decompress(fr, decompressed_size=len(d)).to_pybytes() == d
+        blob = pyref.blob_encode(d)
+        comp = blob[:8] == pyref.BLOB_MAGIC_COMPRESSED
+        assert comp == (len(fr) < len(d)) and len(blob) == 12 + (len(fr) if comp else len(d))
+    assert pyref.blob_encode(b"") == pyref.BLOB_MAGIC_UNCOMPRESSED + bytes(4)
+    assert len(pyref.zstd_frame_rle_raw(b"\0" * (4 << 20))) == 13 + 32 * 4
