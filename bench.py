@@ -232,7 +232,7 @@ def h2d_roofline(torch, host_arr, nbytes=8 << 30):
     return best
 
 
-def run_distinct(args, eng, pg, torch, cfg, total_gib=768, batch_files=256, nbuf=6, early=True):
+def run_distinct(args, eng, pg, torch, cfg, total_gib=768, batch_files=256, nbuf=7, early=True):
     """value_distinct: the same path over NON-REPEATING data (the cfg3 corpus): every batch is generated on the device,
     hashed ONCE, and its buffer is refilled as soon as the device no longer reads it -- with `early` (the default,
     PBSGPU_BATCH_EARLY_INPUT) that is when the bulk pass and the copy of the long chunks into the library's arena are done,
@@ -806,7 +806,7 @@ def main():
     ap.add_argument("--no-verify", action="store_true", help="skip the untimed post-run comparison with the oracle")
     ap.add_argument("--no-distinct", action="store_true", help="skip the non-repeating-data figure (value_distinct)")
     ap.add_argument("--distinct-gib", type=int, default=768)
-    ap.add_argument("--distinct-bufs", type=int, default=6, help="16 GiB input buffers of the value_distinct run")
+    ap.add_argument("--distinct-bufs", type=int, default=7, help="16 GiB input buffers of the value_distinct run")
     ap.add_argument("--distinct-batch-files", type=int, default=256, help="files (of --file-mib) per batch of the value_distinct run")
     ap.add_argument("--distinct-early", type=int, default=1, help="0: value_distinct without PBSGPU_BATCH_EARLY_INPUT")
     ap.add_argument("--total-tb", type=float, default=10.0, help="cfg3 only")
