@@ -562,6 +562,7 @@ static bool arena_reserve(pbsgpu_job *j, cudaStream_t side) {
         if (!j->d_arena_off || !j->h_early) return false;
     }
     uint64_t need = j->total_bytes / 16 * (uint64_t)ctx->arena_frac_x16 + (uint64_t)j->cfg.max + 4096;
+    need = std::max<uint64_t>(need, 16ull << 20);   // a granule: bounds the number of live records (and their events) for tiny jobs
     need = std::min((need + 255) & ~255ull, ctx->arena_bytes & ~255ull);
     if (ctx->arena_cursor + need > ctx->arena_bytes) ctx->arena_cursor = 0;
     const uint64_t lo = ctx->arena_cursor, hi = lo + need;

@@ -305,29 +305,30 @@ def _early_engine(**env):
             del os.environ[k]
 
 
-def _mixed_streams(seed, n=6, size=3_000_000):
+def _mixed_streams(seed, n=6, size=3_000_000, zeros=1_200_000):
     """random data (a few long chunks), zero runs (every chunk at max: all of them 'long') and short files"""
     arrs = []
     for i in range(n):
         a = rnd(size + 4099 * i, seed * 100 + i)
         if i % 2:
-            a[size // 3: size // 3 + 1_200_000] = 0
+            a[size // 3: size // 3 + zeros] = 0
         arrs.append(a)
     arrs.append(rnd(77, seed * 100 + 50))
     arrs.append(np.zeros(0, dtype=np.uint8))
     return arrs
 
 
-@pytest.mark.parametrize("env", [{}, {"PBSGPU_ARENA_FRAC_X16": 1, "PBSGPU_ARENA_MB": 256}],
+@pytest.mark.parametrize("env,size,zeros", [({}, 3_000_000, 1_200_000),
+                                            ({"PBSGPU_ARENA_FRAC_X16": 1, "PBSGPU_ARENA_MB": 256}, 10_000_000, 5_000_000)],
                          ids=["default-arena", "tight-reservation"])
-def test_early_input_release_lets_the_caller_overwrite_the_buffer(torch, env):
+def test_early_input_release_lets_the_caller_overwrite_the_buffer(torch, env, size, zeros):
     """PBSGPU_BATCH_EARLY_INPUT: after wait_input the buffer is overwritten while the long chunks' chains still run --
-    they read the arena copy -- and the records still equal the oracle's.  The tight reservation (1/16 of the bytes + one
-    maximum chunk) does not hold every long chunk: the plan trims the head and the rest stays with the bulk pass."""
+    they read the arena copy -- and the records still equal the oracle's.  The tight reservation (the 16 MiB granule for
+    ~20 MB of long chunks) does not hold every long chunk: the plan trims the head and the rest stays with the bulk pass."""
     e = _early_engine(**env)
     try:
         cfg, cfg_o = pg.make_config(1 << 16), oracle.config(1 << 16)
-        arrs = _mixed_streams(1)
+        arrs = _mixed_streams(1, size=size, zeros=zeros)
         buf, off, ln = pack(arrs, align=1)           # unaligned chunk starts: the copy keeps the misalignment mod 16
         ref = oracle.chunk_digest_streams(cfg_o, arrs)
         assert len(ref) > 100
