@@ -54,6 +54,9 @@ class DedupWriter:
     config: Cfg
     known: DigestSet | None = None
     upload: Callable[[bytes, bytes], None] | None = None   # (digest, chunk bytes) for NEW chunks
+    # (digest, DataBlob) for NEW chunks: the body of POST /dynamic_chunk (log_cleanup.go:19-31), rendered for all new
+    # chunks of a flush by ONE pbsgpu_blob_encode_batch_z call (zstd frame where smaller, CRC-32 from the GPU)
+    upload_blob: Callable[[bytes, bytes], None] | None = None
     batch_bytes: int = 1 << 30
     index: list[IndexRecord] = field(default_factory=list)
     # relPath -> XXH3-64 of the file as uploaded: commitWalkState.backedHashes (commit.go:187, :725), computed on the
@@ -82,25 +85,33 @@ class DedupWriter:
         if not self._pending:
             return
         entries, arrs = zip(*self._pending)
-        rec, hashes = self._batch(arrs)
+        buf, offs, lens = self._pack(arrs)
+        rec, hashes = self.engine.chunk_digest_batch_xxh3(self.config, buf, offs, lens, self.known)
         for e, h in zip(entries, hashes):
             self.backed_hashes[e.Path] = int(h)
+        new_chunks = []                                   # (digest, stream, start, end) of the chunks the server lacks
+        starts: dict[int, int] = {}
         for r in rec:
             i = int(r["stream"])
             known = bool(r["flags"] & CHUNK_KNOWN)
-            self.index.append(IndexRecord(entries[i].Path, int(r["end_off"]), bytes(r["digest"]), known))
+            s0, e0 = starts.get(i, 0), int(r["end_off"])
+            starts[i] = e0
+            self.index.append(IndexRecord(entries[i].Path, e0, bytes(r["digest"]), known))
+            if not known:
+                new_chunks.append((bytes(r["digest"]), i, s0, e0))
         if self.upload is not None:
-            starts: dict[int, int] = {}
-            for r in rec:
-                i = int(r["stream"])
-                s = starts.get(i, 0)
-                e = int(r["end_off"])
-                if not (r["flags"] & CHUNK_KNOWN):
-                    self.upload(bytes(r["digest"]), arrs[i][s:e].tobytes())
-                starts[i] = e
+            for d, i, s0, e0 in new_chunks:
+                self.upload(d, arrs[i][s0:e0].tobytes())
+        if self.upload_blob is not None and new_chunks:
+            boff = np.array([int(offs[i]) + s0 for _, i, s0, _ in new_chunks], dtype=np.uint64)
+            blen = np.array([e0 - s0 for _, _, s0, e0 in new_chunks], dtype=np.uint64)
+            blobs, _crc = self.engine.blob_encode_batch_z(buf, boff, blen)
+            for (d, _i, _s, _e), blob in zip(new_chunks, blobs):
+                self.upload_blob(d, blob)
         self._pending, self._pending_bytes = [], 0
 
-    def _batch(self, arrs):
+    @staticmethod
+    def _pack(arrs):
         lens = np.array([len(a) for a in arrs], dtype=np.uint64)
         offs = np.zeros(len(arrs), dtype=np.uint64)
         pos = 0
@@ -110,7 +121,7 @@ class DedupWriter:
         buf = np.zeros(max(pos, 1), dtype=np.uint8)
         for a, o in zip(arrs, offs):
             buf[int(o): int(o) + len(a)] = a
-        return self.engine.chunk_digest_batch_xxh3(self.config, buf, offs, lens, self.known)
+        return buf, offs, lens
 
     def Finish(self) -> list[IndexRecord]:
         self.Flush()
@@ -244,14 +255,14 @@ class PayloadStreamWriter:
 
 
 def NewRemoteDedupSplitArchiveWriter(engine: Engine, config: Cfg, known: DigestSet | None = None,
-                                     orig_payload_idx: bytes | None = None, upload=None) -> DedupWriter:
+                                     orig_payload_idx: bytes | None = None, upload=None, upload_blob=None) -> DedupWriter:
     """commit.go:329.  `orig_payload_idx` = bytes of the previous .ppxar.didx (commit.go:324-328):
     its digests seed the known set, so unchanged chunks are not uploaded again."""
     if orig_payload_idx:
         if known is None:
             known = engine.digest_set()
         known.seed_didx(orig_payload_idx)
-    return DedupWriter(engine, config, known, upload)
+    return DedupWriter(engine, config, known, upload, upload_blob)
 
 
 def verifyBackedFileHashes(engine: Engine, open_file: Callable[[str], BinaryIO], hashes: dict[str, int],

@@ -530,6 +530,32 @@ def test_blob_encode_batch_z_on_chunker_output(eng, torch):
     assert total < len(img) * 0.6                     # ~11 of 24 MiB are zero runs
 
 
+def test_dedup_writer_uploads_datablobs_rendered_on_the_gpu(eng, torch):
+    """The writer mirror with `upload_blob`: chunk + digest + probe + XXH3 in one call, then ONE blob_encode_batch_z for the
+    chunks the server lacks -- the bodies equal the restated DataBlob encoding of exactly those chunks."""
+    from oracle import pyref
+    blobs = []
+    w = transfer.NewRemoteDedupSplitArchiveWriter(eng, pg.make_config(1 << 16), known=eng.digest_set(),
+                                                  upload_blob=lambda d, b: blobs.append((d, b)))
+    sparse = rnd(6_000_000, 90)
+    sparse[1_000_000:4_500_000] = 0
+    files = [("disk.img", sparse), ("copy.img", sparse.copy()), ("small", rnd(100, 91))]
+    for name, data in files:
+        w.WriteEntry(transfer.Entry(name, len(data)), data.tobytes())
+    idx = w.Finish()
+    ref = oracle.chunk_digest_streams(oracle.config(1 << 16), [d for _, d in files])
+    assert [(r.end_off, r.digest) for r in idx] == [(int(r["end_off"]), bytes(r["digest"])) for r in ref]
+    want, seen, start = [], set(), {}
+    for r in ref:
+        i = int(r["stream"]); s0 = start.get(i, 0); e0 = int(r["end_off"]); start[i] = e0
+        d = bytes(r["digest"])
+        if d not in seen:
+            seen.add(d)
+            want.append((d, pyref.blob_encode(files[i][1][s0:e0].tobytes())))
+    assert blobs == want
+    assert any(b[:8] == pyref.BLOB_MAGIC_COMPRESSED for _, b in blobs)
+
+
 # ---- e: the NCCL merge through the C ABI ------------------------------------------------------------------------------
 def test_set_allgather_single_rank_equals_insert(eng):
     """World of one: pbsgpu_set_allgather must behave exactly like pbsgpu_set_insert (also proves that libnccl resolves

@@ -34,6 +34,12 @@ class OracleEngine:
     def xxh3_batch(self, buf, off, length):
         return np.array([oracle.xxh3_64(np.asarray(buf[int(o): int(o + l)])) for o, l in zip(off, length)], dtype=np.uint64)
 
+    def blob_encode_batch_z(self, buf, off, length):
+        from oracle import pyref
+        import zlib
+        blobs = [pyref.blob_encode(np.asarray(buf[int(o): int(o + l)]).tobytes()) for o, l in zip(off, length)]
+        return blobs, np.array([zlib.crc32(b[12:]) for b in blobs], dtype=np.uint32)
+
     def digest_set(self, hint=0):
         class S:
             def __init__(s): s.s = oracle.DigestSet()
@@ -77,6 +83,38 @@ def test_dedup_writer_flow_index_order_and_upload_only_new():
     assert w.backed_hashes == {name: oracle.xxh3_64(data) for name, data in files}   # ow.backedHashes, commit.go:725
     with pytest.raises(RuntimeError):
         w.WriteEntry(transfer.Entry("late", 1), b"x")
+
+
+def test_dedup_writer_renders_datablobs_for_new_chunks_only():
+    """upload_blob: the POST /dynamic_chunk bodies of the chunks the server lacks, one batched render per flush; zero runs
+    come out as compressed blobs."""
+    from oracle import pyref
+    eng = OracleEngine()
+    blobs = []
+    w = transfer.NewRemoteDedupSplitArchiveWriter(eng, buzhash.NewConfigBytes(65536), known=eng.digest_set(),
+                                                  upload_blob=lambda d, b: blobs.append((d, b)))
+    sparse = rnd(3_000_000, 4)
+    sparse[500_000:2_200_000] = 0
+    files = [("disk.img", sparse), ("copy.img", sparse.copy()), ("small", rnd(100, 5))]
+    for name, data in files:
+        w.WriteEntry(transfer.Entry(name, len(data)), data.tobytes())
+    idx = w.Finish()
+    new = [r for r in idx if not r.known]
+    assert [d for d, _ in blobs] == [r.digest for r in new]            # in index order, new chunks only
+    assert all(r.known for r in idx if r.path == "copy.img")
+    ends = {}
+    n_comp = 0
+    for r, (_, blob) in zip(new, blobs):
+        data = dict(files)[r.path]
+        s0 = ends.get(r.path, 0)
+        for q in idx:                                                    # start = previous end of the same file
+            if q.path == r.path and q.end_off < r.end_off:
+                s0 = max(s0, q.end_off)
+        chunk = data[s0: r.end_off].tobytes()
+        assert hashlib.sha256(chunk).digest() == r.digest
+        assert blob == pyref.blob_encode(chunk)
+        n_comp += blob[:8] == pyref.BLOB_MAGIC_COMPRESSED
+    assert n_comp >= 1 and sum(len(b) for _, b in blobs) < len(sparse) - 1_000_000
 
 
 def test_short_reader_is_an_error_like_io_readfull():
