@@ -105,6 +105,21 @@ def test_split_invariance_of_streaming_scan():
         assert oracle.chunk_ends(cfg, data, feed=feed).tolist() == ref, feed
 
 
+def test_upstream_chunker_self_test_input():
+    """The input of upstream's own chunker unit test (pbs-datastore chunker.rs `test_chunker1`: the little-endian u32
+    counter 0..256Ki, average 64 KiB, fed one byte at a time and then in one piece -- it asserts that both feeds cut
+    alike and that the chunks add up; it holds no golden offsets).  Same assertions here, plus the three restatements."""
+    data = np.arange(256 * 1024, dtype="<u4").view(np.uint8)
+    cfg = oracle.config(64 * 1024)
+    whole = oracle.chunk_ends(cfg, data).tolist()
+    assert oracle.chunk_ends(cfg, data, feed=1).tolist() == whole
+    assert whole[-1] == len(data) == 1 << 20
+    lens = np.diff([0] + whole)
+    assert (lens[:-1] >= cfg.min).all() and (lens <= cfg.max).all()
+    assert oracle.chunk_ends_closed_form(cfg, data).tolist() == whole
+    assert pyref.chunk_ends(oracle.default_table(), data, 64 * 1024) == whole
+
+
 def test_min_max_invariants_and_forced_cuts():
     cfg = oracle.config(256)
     # constant data: H == 0 for a full window, never passes the test -> every cut is forced at max
